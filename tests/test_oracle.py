@@ -1,0 +1,140 @@
+"""CPU tests that PIN the oracle (oracle/xlating_oracle.c, lpf_oracle.c):
+
+1. against every golden vector the reference's own tests hold for this path
+   (tests/golden/reference_fixtures.json, extracted from test/test_xlating.c,
+   test/test_lpf.c, test/test_tcp_server.c) with the reference's own assert
+   semantics (test/utils.c:176-196);
+2. bit-for-bit against the reference itself (oracle/_ref/libref_strict.so,
+   compiled from /root/reference by oracle/Makefile) on seeded random streams.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+
+def trunc4(x):
+    """(int32)(x*10000) as the reference's assert_cf32 does (test/utils.c:179)."""
+    return (np.asarray(x, dtype=np.float32) * np.float32(10000)).astype(np.int32)
+
+
+def ramp(fmt, offset, n):
+    """test/utils.c:137-165"""
+    i = np.arange(n, dtype=np.int64) + offset
+    if fmt == "cu8":
+        return (i & 0xFF).astype(np.uint8)
+    if fmt == "cs8":
+        return (i & 0xFF).astype(np.uint8).view(np.int8)
+    return ((i & 0xFFFF).astype(np.uint16).view(np.int16) - np.int16(n // 2)).astype(np.int16)
+
+
+def make_filter(fx, max_input):
+    s = fx["xlating"]["setup"]
+    taps = po.lpf_design(s["lpf"]["gain"], s["sampling_freq"], s["lpf"]["cutoff"], s["lpf"]["transition_width"])
+    assert len(taps) == s["ntaps"]
+    return po.OracleFilter(s["decimation"], taps, s["center_freq"], s["sampling_freq"], max_input)
+
+
+def test_lpf_golden(fixtures):
+    g = fixtures["lpf"]
+    a = g["args"]
+    taps = po.lpf_design(a["gain"], a["sampling_freq"], a["cutoff"], a["transition_width"])
+    assert len(taps) == g["ntaps"]
+    np.testing.assert_array_equal(trunc4(taps), trunc4(g["taps"]))
+    for fs, cutoff, tw in g["bad_args"]:
+        with pytest.raises(ValueError):
+            po.lpf_design(1.0, fs, cutoff, tw)
+
+
+def test_xlating_full_block_golden(fixtures):
+    g = fixtures["xlating"]["max_input_buffer_size"]
+    f = make_filter(fixtures, g["max_input"])
+    x = ramp("cu8", 0, g["input_len"])
+    y = f.process_cf32("cu8", x)
+    assert len(y) == len(g["cf32"]) // 2
+    np.testing.assert_array_equal(trunc4(y.view(np.float32)), trunc4(g["cf32"]))
+    q = f.process_q15("cu8", x)
+    np.testing.assert_array_equal(q.reshape(-1), np.array(g["cs16"], dtype=np.int16))
+
+
+def test_xlating_partial_blocks_golden(fixtures):
+    g = fixtures["xlating"]["partial_input_buffer_size"]
+    f = make_filter(fixtures, g["max_input"])
+    x0 = ramp("cu8", 0, g["input_len"])
+    y = f.process_cf32("cu8", x0)
+    np.testing.assert_array_equal(trunc4(y.view(np.float32)), trunc4(g["cf32"]))
+    q = f.process_q15("cu8", x0)
+    np.testing.assert_array_equal(q.reshape(-1), np.array(g["cs16"], dtype=np.int16))
+    x1 = ramp("cu8", 200, g["input_len"])
+    y = f.process_cf32("cu8", x1)
+    np.testing.assert_array_equal(trunc4(y.view(np.float32)), trunc4(g["next_cf32"]))
+    q = f.process_q15("cu8", x1)
+    np.testing.assert_array_equal(q.reshape(-1), np.array(g["next_cs16"], dtype=np.int16))
+
+
+def test_xlating_small_input_golden(fixtures):
+    g = fixtures["xlating"]["small_input_data"]
+    f = make_filter(fixtures, g["max_input"])
+    x = ramp("cu8", 0, g["first_len"])
+    f.process_cf32("cu8", x)
+    f.process_q15("cu8", x)
+    x = ramp("cu8", 200, g["second_len"])
+    assert len(f.process_cf32("cu8", x)) == g["expected_outputs"]
+    assert len(f.process_q15("cu8", x)) == g["expected_outputs"]
+
+
+@pytest.mark.parametrize("fmt,key", [("cu8", "rtlsdr_cu8"), ("cs16", "airspy_cs16"), ("cs8", "hackrf_cs8")])
+def test_tcp_server_goldens(fixtures, fmt, key):
+    """test/test_tcp_server.c:154-248 reproduced without the socket plumbing:
+    dsp_worker_start's filter (src/dsp_worker.c:98-104) on the mock SDR ramps."""
+    s = fixtures["tcp_server"]["setup"]
+    taps = po.lpf_design(1.0, s["band_sampling_rate"], s["lpf"]["cutoff"], s["lpf"]["transition_width"])
+    assert len(taps) == s["ntaps"]
+    f = po.OracleFilter(s["decimation"], taps, s["center_offset"], s["band_sampling_rate"], s["buffer_size"])
+    y = f.process_cf32(fmt, ramp(fmt, 0, s["input_elements"]))
+    exp = np.array(fixtures["tcp_server"][key], dtype=np.float32)
+    assert len(y) == len(exp) // 2
+    np.testing.assert_array_equal(trunc4(y.view(np.float32)), trunc4(exp))
+
+
+needs_ref = pytest.mark.skipif(not po.ref_available("strict"), reason="oracle/_ref not built (no /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("fs,cutoff,tw", [(8000, 1750, 500), (48000, 4800, 2000), (2016000, 24000, 16400),
+                                          (2016000, 24000, 9600), (2016000, 24000, 2000), (10000000, 125000, 20060),
+                                          (61440000, 24000, 9600)])
+def test_lpf_bit_exact_vs_reference(fs, cutoff, tw):
+    a = po.lpf_design(1.0, fs, cutoff, tw)
+    b = po.ref_lpf_design(1.0, fs, cutoff, tw)
+    assert a.tobytes() == b.tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("fmt", ["cu8", "cs8", "cs16"])
+@pytest.mark.parametrize("fs,rate,tw,center", [(48000, 9600, 2000, -12000), (2016000, 48000, 16400, -312000),
+                                               (2016000, 96000, 19200, 400123), (10000000, 250000, 50000, 1234567)])
+def test_stream_bit_exact_vs_reference(fmt, fs, rate, tw, center):
+    """Ragged multi-call streams: restatement == compiled reference, bit for bit,
+    for the float path (incl. phase recursion + renormalisation) and the Q15 path."""
+    rng = np.random.default_rng(1234)
+    taps = po.lpf_design(1.0, fs, rate // 2, tw)
+    D = fs // rate
+    max_in = 40000
+    fo = po.OracleFilter(D, taps, center, fs, max_in)
+    fr = po.RefFilter(D, taps, center, fs, max_in)
+    qo = po.OracleFilter(D, taps, center, fs, max_in)
+    qr = po.RefFilter(D, taps, center, fs, max_in)
+    for n in [40000, 2, 38, 12346, 0, 40000, 20000, 4, 39998, 40000]:
+        if fmt == "cs16":
+            x = rng.integers(-32768, 32768, n, dtype=np.int16)
+        elif fmt == "cs8":
+            x = rng.integers(-128, 128, n, dtype=np.int8)
+        else:
+            x = rng.integers(0, 256, n, dtype=np.uint8)
+        a = fo.process_cf32(fmt, x)
+        b = fr.process_cf32(fmt, x)
+        assert a.tobytes() == b.tobytes()
+        a = qo.process_q15(fmt, x)
+        b = qr.process_q15(fmt, x)
+        assert a.tobytes() == b.tobytes()
