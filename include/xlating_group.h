@@ -1,0 +1,122 @@
+/*
+ * include/xlating_group.h -- batch extension of the xlating C ABI: MANY clients
+ * (channels) decimating ONE wideband IQ stream on one GPU.
+ *
+ * Why it exists.  In the reference every client owns a filter and a dsp thread,
+ * and every SDR block is memcpy'd once per client (src/tcp_server.c:262-269 ->
+ * src/queue.c:114) and converted + filtered once per client on the CPU
+ * (src/dsp_worker.c:49-72 -> src/xlating.c:384-414).  Through the per-filter ABI
+ * (include/xlating.h) a GPU library cannot know that C callers hold copies of
+ * the SAME block, so this header adds the entry points a maintainer binds in
+ * sdr_callback/dsp_worker: the block is submitted ONCE,
+ * staged into HBM with one pinned async copy, converted once, and all clients'
+ * NCO-mix + FIR + decimate run as one fused launch
+ * (sdr-server_b200/csrc/xlating_kernels.cuh); each dsp thread then only waits
+ * for its ticket and writes its own output.
+ *
+ * Semantics per client are exactly those of include/xlating.h (history, phase
+ * recursion, per-call renormalisation, output counts): a client added at stream
+ * position P behaves like a reference filter created at that moment (zero
+ * history before P), cf. src/xlating.c:543-565.
+ *
+ * All functions return 0 (or a non-negative ticket) on success and a negative
+ * errno-style code on failure, logging "<3>..." to stderr like the reference
+ * (src/dsp_worker.c:17).  A group is NOT thread-safe for submit/add/remove
+ * (one producer, like the single SDR thread); xlg_wait/xlg_output may be called
+ * concurrently from many consumer threads.
+ */
+#ifndef XLATING_B200_GROUP_H_
+#define XLATING_B200_GROUP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xlg_group xlg_group;
+
+/* input sample formats = the three SDR front-ends (src/sdr_device.c; cu8 RTL-SDR,
+ * cs8 HackRF, cs16 Airspy) */
+enum { XLG_FMT_CU8 = 0, XLG_FMT_CS8 = 1, XLG_FMT_CS16 = 2 };
+
+/* xlg_create flags */
+#define XLG_OUT_DEVICE 0x1u    /* leave outputs in HBM (no D2H); xlg_output returns device pointers */
+#define XLG_NO_RENORM 0x2u     /* skip the per-call phase renormalisation (AVX variant, src/xlating.c:336-339) */
+#define XLG_FORCE_GENERIC 0x4u /* route every client through the generic kernel (testing) */
+/* xlg_submit flags */
+#define XLG_INPUT_DEVICE 0x100u /* `input` is a device pointer on the group's GPU (already staged) */
+#define XLG_PATH_Q15 0x200u     /* Q15 integer path (src/xlating.c:92-140) instead of cf32 */
+
+/* number of blocks that may be in flight; outputs of ticket t stay valid until
+ * ticket t + XLG_SLOTS is submitted */
+#define XLG_SLOTS 4
+
+/* One wideband stream on CUDA device `device`.  max_input_len is the largest
+ * block, in scalar elements (like create_frequency_xlating_filter's
+ * max_input_buffer_length, src/xlating.c:553). */
+int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input_len, uint32_t flags, xlg_group **out);
+void xlg_destroy(xlg_group *g);
+
+/* Attach / detach a client.  Arguments as create_frequency_xlating_filter
+ * (src/xlating.c:495); `taps` is copied, not adopted.  *client_id is a small
+ * non-negative handle, stable until removed. */
+int xlg_add_client(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len,
+                   int32_t center_freq, int *client_id);
+int xlg_remove_client(xlg_group *g, int client_id);
+int xlg_client_count(const xlg_group *g);
+
+/* Submit one block for ALL clients.  `input_len` in scalar elements.  Returns a
+ * ticket (0,1,2,...) immediately; work proceeds asynchronously.  Blocks when
+ * XLG_SLOTS tickets are already in flight and the oldest has not completed. */
+int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t input_len, uint32_t flags);
+
+/* Block until ticket's outputs are complete (in pinned host memory, or in HBM
+ * with XLG_OUT_DEVICE). */
+int xlg_wait(xlg_group *g, int64_t ticket);
+
+/* Output of one client for a completed ticket: cf32 (interleaved float re,im) or,
+ * for XLG_PATH_Q15 tickets, int16 re,im pairs.  *out_len counts complex samples
+ * and is available right after xlg_submit returns (it is computed on the host). */
+int xlg_output(xlg_group *g, int64_t ticket, int client_id, const void **out, size_t *out_len);
+
+/* Pinned host memory for input blocks (queue/ingest buffers). */
+void *xlg_alloc_pinned(size_t bytes);
+void xlg_free_pinned(void *p);
+
+/* Make the group's work wait for everything already enqueued on an external
+ * CUDA stream (e.g. the torch/NCCL stream that produced a device input). */
+int xlg_wait_stream(xlg_group *g, void *cuda_stream);
+
+/* Device-side timing of a region of submits: xlg_timer_start drains the group
+ * and records a start event; xlg_timer_stop records an end event that depends
+ * on all work submitted so far, synchronises and returns elapsed milliseconds. */
+int xlg_timer_start(xlg_group *g);
+int xlg_timer_stop(xlg_group *g, float *elapsed_ms);
+
+/* Per-kernel profiling (CUDA events around each launch on its own stream).
+ * Counters accumulate while enabled and are harvested by xlg_wait. */
+typedef struct {
+  double fir_tile_ms;    /* tiled multi-client FIR kernel (dominant) */
+  double fir_generic_ms; /* generic split-K FIR kernel */
+  double phase_ms;       /* oscillator pre-pass */
+  double convert_ms;     /* raw -> cf32 ring */
+  uint64_t fir_tile_launches, fir_generic_launches, phase_launches, convert_launches;
+  uint64_t blocks;       /* submitted blocks accounted */
+  uint64_t out_samples;  /* complex outputs produced (all clients) */
+  uint64_t in_samples;   /* complex inputs consumed */
+  uint64_t tile_macs;    /* complex MACs issued by the tiled kernel incl. padding */
+  uint64_t algo_macs;    /* algorithmic complex MACs: sum n_out * taps_len */
+} xlg_profile;
+int xlg_profile_enable(xlg_group *g, int on);
+int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset);
+
+/* Introspection for tests: history length (src/xlating.c:29 history_offset) and
+ * which kernel currently serves the client (0 = generic, 1 = tiled). */
+int xlg_client_info(const xlg_group *g, int client_id, size_t *history, int *kernel_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XLATING_B200_GROUP_H_ */

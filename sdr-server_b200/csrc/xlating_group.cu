@@ -1,0 +1,951 @@
+/*
+ * csrc/xlating_group.cu -- host side of the batch C ABI (include/xlating_group.h):
+ * one wideband stream, many clients, one GPU.
+ *
+ * Data layout in HBM (per group):
+ *   ring / qring     power-of-two ring of converted samples (float2 / short2); the
+ *                    absolute stream index s lives at ring[s & mask].  Holds the
+ *                    in-flight blocks plus the longest history (T-1 samples), so
+ *                    history never has to be moved (the reference memmoves it
+ *                    every call, src/xlating.c:76-79).
+ *   clients          ClientDev table: decimation phase (hist), oscillator, offsets
+ *   taps / qtaps     reversed band-pass taps per client, natural order
+ *   tile_taps        the same taps re-packed [class][group of 32][flat tap][32]
+ *                    for the tiled kernel's TMA chunks
+ *   per slot (XLG_SLOTS in flight): raw input staging, BlkInfo, per-output
+ *                    oscillator table, output arena (+ pinned host mirrors)
+ *
+ * Streams: s_in (H2D), s_ph (oscillator pre-pass chain), s_c (convert + FIR),
+ * s_out (D2H); events order them per block so block b+1's copy and pre-pass
+ * overlap block b's FIR.
+ *
+ * The reference's per-client dsp loop this replaces: src/dsp_worker.c:41-88 calling
+ * src/xlating.c:384-414 -> :52-83 once per client per block.
+ */
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "taps_host.h"
+#include "xlating_group.h"
+#include "xlating_kernels.cuh"
+
+using namespace xl;
+
+#define XL_LOG(...)                   \
+  do {                                \
+    fprintf(stderr, "<3>xlating_b200: " __VA_ARGS__); \
+    fprintf(stderr, "\n");            \
+  } while (0)
+
+#define CU_OK(expr)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      XL_LOG("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return -EIO;                                                                       \
+    }                                                                                    \
+  } while (0)
+
+namespace {
+
+constexpr int kTileMinClients = 8;     // smaller aligned classes go to the generic kernel
+constexpr int kTileMinOutputs = 48;    // per block; below this a 128-output tile is mostly idle
+constexpr int kTileMaxSmem = 200 * 1024;
+
+struct HostClient {
+  bool active = false;
+  uint32_t D = 0;
+  size_t T = 0;
+  std::vector<float> rev;        // 2*T
+  std::vector<int16_t> rev_q15;  // 2*T
+  float incr_re = 0, incr_im = 0;
+  int16_t qincr_re = 0, qincr_im = 0;
+  long long hist = 0;            // mirror of ClientDev::hist
+  long long zero_before = 0, qzero_before = 0;
+  bool is_new = true;            // dynamic state not yet on the device
+  int kind = 0;
+  int out_off = 0, out_cap = 0;
+  int taps_off = 0;
+};
+
+struct Slot {
+  void *d_raw = nullptr, *h_raw = nullptr;
+  float2 *d_out = nullptr, *h_out = nullptr;
+  short2 *d_qout = nullptr, *h_qout = nullptr;
+  float2 *d_phases = nullptr;
+  short2 *d_qphases = nullptr;
+  BlkInfo *d_blk = nullptr;
+  size_t blk_cap = 0;
+  cudaEvent_t ev_h2d = nullptr, ev_conv = nullptr, ev_phase = nullptr, ev_fir = nullptr, ev_done = nullptr;
+  cudaEvent_t pf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pf_conv = false, pf_phase = false, pf_tile = false, pf_gen = false;
+  int64_t ticket = -1;
+  bool q15 = false;
+  bool harvested = true;
+  std::vector<int> n_out;    // per client id
+  std::vector<int> out_off;  // per client id
+  uint64_t tile_macs = 0, algo_macs = 0, out_samples = 0, in_samples = 0;
+};
+
+struct TileClassHost {
+  TileClass k;
+  std::vector<int> members;
+  size_t T;
+};
+
+}  // namespace
+
+struct xlg_group {
+  int device = 0;
+  uint32_t fs = 0;
+  uint32_t max_input_len = 0;  // scalar elements
+  uint32_t flags = 0;
+  cudaStream_t s_in = nullptr, s_ph = nullptr, s_c = nullptr, s_out = nullptr;
+
+  float2 *ring = nullptr;
+  short2 *qring = nullptr;
+  size_t ring_cap = 0;    // samples, power of two
+  size_t hist_cap = 0;    // longest T-1 the ring was sized for
+  long long S = 0, qS = 0;  // absolute stream positions of the two paths
+
+  std::vector<HostClient> clients;
+  ClientDev *d_clients = nullptr;
+  size_t d_clients_cap = 0;
+  float2 *d_taps = nullptr;
+  short2 *d_qtaps = nullptr;
+  float2 *d_tile_taps = nullptr;
+  int *d_members = nullptr;
+  size_t arena_cap = 0;   // complex samples per slot arena
+  bool q_alloc = false;
+
+  std::vector<TileClassHost> classes;
+  int n_generic = 0;
+  int max_client = 0;     // highest active id + 1
+  bool dirty = true;
+
+  Slot slots[XLG_SLOTS];
+  int64_t next_ticket = 0;
+  cudaEvent_t ev_last_conv = nullptr;  // conversion of the previous block (history dependency)
+  bool have_last_conv = false;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+
+  bool profiling = false;
+  xlg_profile prof;
+  std::mutex mu;  // guards slots' harvest + profile
+};
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static size_t next_pow2(size_t v) {
+  size_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int elem_bytes(int fmt) { return fmt == XLG_FMT_CS16 ? 2 : 1; }
+
+static void slot_free(Slot &s) {
+  if (s.d_raw) cudaFree(s.d_raw);
+  if (s.h_raw) cudaFreeHost(s.h_raw);
+  if (s.d_out) cudaFree(s.d_out);
+  if (s.h_out) cudaFreeHost(s.h_out);
+  if (s.d_qout) cudaFree(s.d_qout);
+  if (s.h_qout) cudaFreeHost(s.h_qout);
+  if (s.d_phases) cudaFree(s.d_phases);
+  if (s.d_qphases) cudaFree(s.d_qphases);
+  if (s.d_blk) cudaFree(s.d_blk);
+  s.d_raw = s.h_raw = nullptr;
+  s.d_out = s.h_out = nullptr;
+  s.d_qout = s.h_qout = nullptr;
+  s.d_phases = nullptr;
+  s.d_qphases = nullptr;
+  s.d_blk = nullptr;
+}
+
+static int drain(xlg_group *g) {
+  CU_OK(cudaStreamSynchronize(g->s_in));
+  CU_OK(cudaStreamSynchronize(g->s_ph));
+  CU_OK(cudaStreamSynchronize(g->s_c));
+  CU_OK(cudaStreamSynchronize(g->s_out));
+  return 0;
+}
+
+static void harvest_locked(xlg_group *g, Slot &s) {
+  if (s.harvested) return;
+  s.harvested = true;
+  if (!g->profiling) return;
+  float ms = 0;
+  if (s.pf_conv && cudaEventElapsedTime(&ms, s.pf[0], s.pf[1]) == cudaSuccess) {
+    g->prof.convert_ms += ms;
+    g->prof.convert_launches++;
+  }
+  if (s.pf_phase && cudaEventElapsedTime(&ms, s.pf[2], s.pf[3]) == cudaSuccess) {
+    g->prof.phase_ms += ms;
+    g->prof.phase_launches++;
+  }
+  if (s.pf_tile && cudaEventElapsedTime(&ms, s.pf[4], s.pf[5]) == cudaSuccess) {
+    g->prof.fir_tile_ms += ms;
+    g->prof.fir_tile_launches++;
+  }
+  if (s.pf_gen && cudaEventElapsedTime(&ms, s.pf[6], s.pf[7]) == cudaSuccess) {
+    g->prof.fir_generic_ms += ms;
+    g->prof.fir_generic_launches++;
+  }
+  g->prof.blocks++;
+  g->prof.out_samples += s.out_samples;
+  g->prof.in_samples += s.in_samples;
+  g->prof.tile_macs += s.tile_macs;
+  g->prof.algo_macs += s.algo_macs;
+}
+
+// (re)allocate the sample rings so that they hold XLG_SLOTS blocks + history
+static int ensure_ring(xlg_group *g, size_t need_hist, bool need_q) {
+  const size_t max_n = g->max_input_len / 2;
+  if (g->ring && need_hist <= g->hist_cap && (!need_q || g->qring)) return 0;
+  const size_t hist_cap = std::max<size_t>(std::max(need_hist, g->hist_cap), 4096);
+  const size_t cap = next_pow2((XLG_SLOTS + 1) * max_n + hist_cap + 64);
+  if (drain(g)) return -EIO;
+  if (!g->ring || cap != g->ring_cap) {
+    float2 *nr = nullptr;
+    CU_OK(cudaMalloc(&nr, cap * sizeof(float2)));
+    CU_OK(cudaMemset(nr, 0, cap * sizeof(float2)));
+    if (g->ring) {
+      // keep the most recent samples at their new ring positions
+      const size_t keep = std::min<size_t>(g->ring_cap, (size_t)std::max<long long>(g->S, 0));
+      std::vector<float2> tmp(g->ring_cap);
+      CU_OK(cudaMemcpy(tmp.data(), g->ring, g->ring_cap * sizeof(float2), cudaMemcpyDeviceToHost));
+      std::vector<float2> fresh(cap, make_float2(0.f, 0.f));
+      for (size_t i = 1; i <= keep; i++) {
+        const unsigned long long ab = (unsigned long long)(g->S - (long long)i);
+        fresh[ab & (cap - 1)] = tmp[ab & (g->ring_cap - 1)];
+      }
+      CU_OK(cudaMemcpy(nr, fresh.data(), cap * sizeof(float2), cudaMemcpyHostToDevice));
+      cudaFree(g->ring);
+    }
+    g->ring = nr;
+    if (g->qring) {
+      short2 *nq = nullptr;
+      CU_OK(cudaMalloc(&nq, cap * sizeof(short2)));
+      const size_t keep = std::min<size_t>(g->ring_cap, (size_t)std::max<long long>(g->qS, 0));
+      std::vector<short2> tmp(g->ring_cap);
+      CU_OK(cudaMemcpy(tmp.data(), g->qring, g->ring_cap * sizeof(short2), cudaMemcpyDeviceToHost));
+      std::vector<short2> fresh(cap, make_short2(0, 0));
+      for (size_t i = 1; i <= keep; i++) {
+        const unsigned long long ab = (unsigned long long)(g->qS - (long long)i);
+        fresh[ab & (cap - 1)] = tmp[ab & (g->ring_cap - 1)];
+      }
+      CU_OK(cudaMemcpy(nq, fresh.data(), cap * sizeof(short2), cudaMemcpyHostToDevice));
+      cudaFree(g->qring);
+      g->qring = nq;
+    }
+    g->ring_cap = cap;
+  }
+  if (need_q && !g->qring) {
+    CU_OK(cudaMalloc(&g->qring, g->ring_cap * sizeof(short2)));
+    CU_OK(cudaMemset(g->qring, 0, g->ring_cap * sizeof(short2)));
+  }
+  g->hist_cap = hist_cap;
+  return 0;
+}
+
+static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
+  const bool dev_out = (g->flags & XLG_OUT_DEVICE) != 0;
+  if (need > g->arena_cap) {
+    const size_t cap = std::max<size_t>(need + need / 4, 1024);
+    for (Slot &s : g->slots) {
+      if (s.d_out) cudaFree(s.d_out);
+      if (s.h_out) cudaFreeHost(s.h_out);
+      if (s.d_phases) cudaFree(s.d_phases);
+      s.d_out = s.h_out = nullptr;
+      s.d_phases = nullptr;
+      CU_OK(cudaMalloc(&s.d_out, cap * sizeof(float2)));
+      CU_OK(cudaMalloc(&s.d_phases, cap * sizeof(float2)));
+      if (!dev_out) CU_OK(cudaHostAlloc(&s.h_out, cap * sizeof(float2), cudaHostAllocDefault));
+      if (g->q_alloc) {
+        if (s.d_qout) cudaFree(s.d_qout);
+        if (s.h_qout) cudaFreeHost(s.h_qout);
+        if (s.d_qphases) cudaFree(s.d_qphases);
+        s.d_qout = s.h_qout = nullptr;
+        s.d_qphases = nullptr;
+        CU_OK(cudaMalloc(&s.d_qout, cap * sizeof(short2)));
+        CU_OK(cudaMalloc(&s.d_qphases, cap * sizeof(short2)));
+        if (!dev_out) CU_OK(cudaHostAlloc(&s.h_qout, cap * sizeof(short2), cudaHostAllocDefault));
+      }
+    }
+    g->arena_cap = cap;
+  }
+  if (need_q && !g->q_alloc) {
+    for (Slot &s : g->slots) {
+      CU_OK(cudaMalloc(&s.d_qout, g->arena_cap * sizeof(short2)));
+      CU_OK(cudaMalloc(&s.d_qphases, g->arena_cap * sizeof(short2)));
+      if (!dev_out) CU_OK(cudaHostAlloc(&s.h_qout, g->arena_cap * sizeof(short2), cudaHostAllocDefault));
+    }
+    g->q_alloc = true;
+  }
+  return 0;
+}
+
+// Re-derive everything that depends on the client set: output offsets, tap
+// arenas, kernel classes.  Dynamic per-client state (hist, phase) lives on the
+// device and is preserved.
+static int rebuild_layout(xlg_group *g) {
+  if (drain(g)) return -EIO;
+  const int nc = (int)g->clients.size();
+  g->max_client = 0;
+  for (int i = 0; i < nc; i++)
+    if (g->clients[i].active) g->max_client = i + 1;
+
+  // 1. current device state
+  std::vector<ClientDev> tab(std::max(nc, 1));
+  memset(tab.data(), 0, tab.size() * sizeof(ClientDev));
+  if (g->d_clients && g->d_clients_cap > 0) {
+    const size_t n = std::min<size_t>(g->d_clients_cap, tab.size());
+    CU_OK(cudaMemcpy(tab.data(), g->d_clients, n * sizeof(ClientDev), cudaMemcpyDeviceToHost));
+  }
+
+  // 2. offsets + natural tap arenas
+  size_t out_total = 0, taps_total = 0, max_hist = 0;
+  for (int i = 0; i < nc; i++) {
+    HostClient &h = g->clients[i];
+    if (!h.active) continue;
+    h.out_cap = (int)(g->max_input_len / 2 / h.D + 2);
+    h.out_off = (int)out_total;
+    out_total += (size_t)h.out_cap;
+    out_total = (out_total + 3) & ~(size_t)3;  // keep rows 32-byte aligned
+    h.taps_off = (int)taps_total;
+    taps_total += h.T;
+    max_hist = std::max(max_hist, h.T - 1);
+  }
+  if (ensure_ring(g, max_hist, g->qring != nullptr)) return -EIO;
+  if (ensure_arenas(g, out_total, g->q_alloc)) return -EIO;
+
+  std::vector<float2> taps(std::max<size_t>(taps_total, 1));
+  std::vector<short2> qtaps(std::max<size_t>(taps_total, 1));
+  for (int i = 0; i < nc; i++) {
+    const HostClient &h = g->clients[i];
+    if (!h.active) continue;
+    for (size_t j = 0; j < h.T; j++) {
+      taps[h.taps_off + j] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+      qtaps[h.taps_off + j] = make_short2(h.rev_q15[2 * j], h.rev_q15[2 * j + 1]);
+    }
+  }
+  if (g->d_taps) cudaFree(g->d_taps);
+  if (g->d_qtaps) cudaFree(g->d_qtaps);
+  g->d_taps = nullptr;
+  g->d_qtaps = nullptr;
+  CU_OK(cudaMalloc(&g->d_taps, taps.size() * sizeof(float2)));
+  CU_OK(cudaMalloc(&g->d_qtaps, qtaps.size() * sizeof(short2)));
+  CU_OK(cudaMemcpy(g->d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(g->d_qtaps, qtaps.data(), qtaps.size() * sizeof(short2), cudaMemcpyHostToDevice));
+
+  // 3. classes for the tiled kernel: identical (D, T, hist) and no pending
+  //    zero-history window (zero_before behind the next window start, or the
+  //    stream origin where the ring itself is still zero)
+  g->classes.clear();
+  g->n_generic = 0;
+  std::map<std::tuple<uint32_t, size_t, long long>, std::vector<int>> buckets;
+  for (int i = 0; i < nc; i++) {
+    HostClient &h = g->clients[i];
+    if (!h.active) continue;
+    h.kind = 0;
+    const long long first = g->S - h.hist;
+    const bool settled = (h.zero_before == 0 && g->S < (long long)g->ring_cap / 2) || h.zero_before <= first;
+    if (!(g->flags & XLG_FORCE_GENERIC) && settled) buckets[std::make_tuple(h.D, h.T, h.hist)].push_back(i);
+  }
+  std::vector<int> members;
+  std::vector<float2> tile_taps;
+  for (auto &kv : buckets) {
+    const uint32_t D = std::get<0>(kv.first);
+    const size_t T = std::get<1>(kv.first);
+    std::vector<int> &ids = kv.second;
+    if ((int)ids.size() < kTileMinClients) continue;
+    const int Dp = (int)(D | 1u);
+    const size_t q_last = (T - 1) / D, r_last = (T - 1) % D;
+    const int L = (int)(((q_last * Dp + r_last + 1) + 7) / 8 * 8);
+    const int xs_len = (T_KT - 1) * Dp + L;
+    const size_t smem = (size_t)T_SMEM_FIXED + (size_t)xs_len * sizeof(float2);
+    const size_t typical_out = g->max_input_len / 2 / D;
+    if (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs) continue;
+    if ((int)g->classes.size() >= T_MAX_CLASSES) continue;
+    TileClassHost ch;
+    memset(&ch.k, 0, sizeof(ch.k));
+    ch.T = T;
+    ch.members = ids;
+    ch.k.D = (int)D;
+    ch.k.Dp = Dp;
+    ch.k.L = L;
+    ch.k.xs_len = xs_len;
+    ch.k.n_groups = (int)((ids.size() + T_CG - 1) / T_CG);
+    ch.k.members_off = (int)members.size();
+    ch.k.taps_off = (long long)tile_taps.size();
+    for (int gi = 0; gi < ch.k.n_groups; gi++) {
+      const size_t base = tile_taps.size();
+      tile_taps.resize(base + (size_t)L * T_CG, make_float2(0.f, 0.f));
+      for (int m = 0; m < T_CG; m++) {
+        const size_t idx = (size_t)gi * T_CG + m;
+        if (idx >= ids.size()) {
+          members.push_back(-1);
+          continue;
+        }
+        const int id = ids[idx];
+        members.push_back(id);
+        g->clients[id].kind = 1;
+        const HostClient &h = g->clients[id];
+        for (size_t j = 0; j < T; j++) {
+          const size_t f = (j / D) * Dp + (j % D);
+          tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+        }
+      }
+    }
+    g->classes.push_back(ch);
+  }
+  // heaviest classes first: their CTAs are scheduled first and the lighter ones
+  // fill the tail of the launch
+  std::sort(g->classes.begin(), g->classes.end(), [](const TileClassHost &a, const TileClassHost &b) {
+    return (long long)a.k.L * T_KT > (long long)b.k.L * T_KT;
+  });
+  if (g->d_tile_taps) cudaFree(g->d_tile_taps);
+  if (g->d_members) cudaFree(g->d_members);
+  g->d_tile_taps = nullptr;
+  g->d_members = nullptr;
+  if (!tile_taps.empty()) {
+    CU_OK(cudaMalloc(&g->d_tile_taps, tile_taps.size() * sizeof(float2)));
+    CU_OK(cudaMemcpy(g->d_tile_taps, tile_taps.data(), tile_taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CU_OK(cudaMalloc(&g->d_members, members.size() * sizeof(int)));
+    CU_OK(cudaMemcpy(g->d_members, members.data(), members.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+
+  // 4. device client table
+  for (int i = 0; i < nc; i++) {
+    HostClient &h = g->clients[i];
+    ClientDev &d = tab[i];
+    if (!h.active) {
+      d.active = 0;
+      continue;
+    }
+    if (h.is_new) {
+      memset(&d, 0, sizeof(d));
+      d.hist = h.hist;
+      d.zero_before = h.zero_before;
+      d.qzero_before = h.qzero_before;
+      d.phase = make_float2(1.0f, 0.0f);  // src/xlating.c:543
+      d.incr = make_float2(h.incr_re, h.incr_im);
+      d.qph_re = INT16_MAX;  // src/xlating.c:546-547
+      d.qph_im = 0;
+      d.qinc_re = h.qincr_re;
+      d.qinc_im = h.qincr_im;
+      h.is_new = false;
+    }
+    d.D = (int)h.D;
+    d.T = (int)h.T;
+    d.taps_off = h.taps_off;
+    d.qtaps_off = h.taps_off;
+    d.out_off = h.out_off;
+    d.out_cap = h.out_cap;
+    d.active = 1;
+    d.kind = h.kind;
+    d.renorm = (g->flags & XLG_NO_RENORM) ? 0 : 1;
+    if (h.kind == 0) g->n_generic++;
+  }
+  if ((size_t)nc > g->d_clients_cap) {
+    if (g->d_clients) cudaFree(g->d_clients);
+    g->d_clients = nullptr;
+    g->d_clients_cap = std::max<size_t>((size_t)nc * 2, 64);
+    CU_OK(cudaMalloc(&g->d_clients, g->d_clients_cap * sizeof(ClientDev)));
+    CU_OK(cudaMemset(g->d_clients, 0, g->d_clients_cap * sizeof(ClientDev)));
+  }
+  if (nc > 0) CU_OK(cudaMemcpy(g->d_clients, tab.data(), (size_t)nc * sizeof(ClientDev), cudaMemcpyHostToDevice));
+
+  for (Slot &s : g->slots) {
+    if (s.blk_cap < (size_t)std::max(nc, 1)) {
+      if (s.d_blk) cudaFree(s.d_blk);
+      s.d_blk = nullptr;
+      s.blk_cap = std::max<size_t>((size_t)nc * 2, 64);
+      CU_OK(cudaMalloc(&s.d_blk, s.blk_cap * sizeof(BlkInfo)));
+    }
+  }
+  g->dirty = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// public API
+// ---------------------------------------------------------------------------
+extern "C" int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input_len, uint32_t flags,
+                          xlg_group **out) {
+  if (out == nullptr || max_input_len < 2 || sampling_freq == 0) return -EINVAL;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    XL_LOG("no usable CUDA device (%s); this library has no CPU fallback",
+           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return -ENODEV;
+  }
+  if (device < 0 || device >= ndev) {
+    XL_LOG("device %d out of range (%d present)", device, ndev);
+    return -ENODEV;
+  }
+  CU_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    XL_LOG("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return -ENODEV;
+  }
+  xlg_group *g = new (std::nothrow) xlg_group();
+  if (g == nullptr) return -ENOMEM;
+  memset(&g->prof, 0, sizeof(g->prof));
+  g->device = device;
+  g->fs = sampling_freq;
+  g->max_input_len = max_input_len;
+  g->flags = flags;
+  int rc = 0;
+  auto fail = [&](int code) {
+    xlg_destroy(g);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->s_c, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(-EIO);
+  const size_t raw_bytes = (size_t)max_input_len * 2;  // cs16 worst case
+  for (Slot &s : g->slots) {
+    if (cudaMalloc(&s.d_raw, raw_bytes) != cudaSuccess) return fail(-ENOMEM);
+    if (cudaHostAlloc(&s.h_raw, raw_bytes, cudaHostAllocDefault) != cudaSuccess) return fail(-ENOMEM);
+    cudaEvent_t *evs[] = {&s.ev_h2d, &s.ev_conv, &s.ev_phase, &s.ev_fir, &s.ev_done};
+    for (cudaEvent_t *ev : evs)
+      if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return fail(-EIO);
+    for (int i = 0; i < 8; i++)
+      if (cudaEventCreate(&s.pf[i]) != cudaSuccess) return fail(-EIO);
+  }
+  if (cudaEventCreateWithFlags(&g->ev_last_conv, cudaEventDisableTiming) != cudaSuccess) return fail(-EIO);
+  if (cudaEventCreate(&g->ev_t0) != cudaSuccess || cudaEventCreate(&g->ev_t1) != cudaSuccess) return fail(-EIO);
+  // the tiled kernel needs > 48 KiB of dynamic shared memory
+  if (cudaFuncSetAttribute(fir_tile_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+      cudaSuccess) {
+    XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
+    return fail(-EIO);
+  }
+  rc = ensure_ring(g, 4096, false);
+  if (rc) return fail(rc);
+  *out = g;
+  return 0;
+}
+
+extern "C" void xlg_destroy(xlg_group *g) {
+  if (g == nullptr) return;
+  cudaSetDevice(g->device);
+  if (g->s_in) cudaStreamSynchronize(g->s_in);
+  if (g->s_ph) cudaStreamSynchronize(g->s_ph);
+  if (g->s_c) cudaStreamSynchronize(g->s_c);
+  if (g->s_out) cudaStreamSynchronize(g->s_out);
+  for (Slot &s : g->slots) {
+    slot_free(s);
+    cudaEvent_t evs[] = {s.ev_h2d, s.ev_conv, s.ev_phase, s.ev_fir, s.ev_done};
+    for (cudaEvent_t ev : evs)
+      if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 8; i++)
+      if (s.pf[i]) cudaEventDestroy(s.pf[i]);
+  }
+  if (g->ev_last_conv) cudaEventDestroy(g->ev_last_conv);
+  if (g->ev_t0) cudaEventDestroy(g->ev_t0);
+  if (g->ev_t1) cudaEventDestroy(g->ev_t1);
+  if (g->ring) cudaFree(g->ring);
+  if (g->qring) cudaFree(g->qring);
+  if (g->d_clients) cudaFree(g->d_clients);
+  if (g->d_taps) cudaFree(g->d_taps);
+  if (g->d_qtaps) cudaFree(g->d_qtaps);
+  if (g->d_tile_taps) cudaFree(g->d_tile_taps);
+  if (g->d_members) cudaFree(g->d_members);
+  if (g->s_in) cudaStreamDestroy(g->s_in);
+  if (g->s_ph) cudaStreamDestroy(g->s_ph);
+  if (g->s_c) cudaStreamDestroy(g->s_c);
+  if (g->s_out) cudaStreamDestroy(g->s_out);
+  delete g;
+}
+
+extern "C" int xlg_add_client(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len,
+                              int32_t center_freq, int *client_id) {
+  if (g == nullptr || client_id == nullptr) return -EINVAL;
+  if (taps_len == 0 || taps == nullptr) return -1;  // src/xlating.c:496
+  if (decimation == 0) return -EINVAL;
+  xl_client_consts k;
+  int rc = xl_client_consts_build(taps, taps_len, decimation, center_freq, g->fs, &k);
+  if (rc) return rc;
+  int id = -1;
+  for (size_t i = 0; i < g->clients.size(); i++)
+    if (!g->clients[i].active) {
+      id = (int)i;
+      break;
+    }
+  if (id < 0) {
+    g->clients.emplace_back();
+    id = (int)g->clients.size() - 1;
+  }
+  HostClient &h = g->clients[id];
+  h = HostClient();
+  h.active = true;
+  h.D = decimation;
+  h.T = taps_len;
+  h.rev.assign(k.rev_cf32, k.rev_cf32 + 2 * taps_len);
+  h.rev_q15.assign(k.rev_q15, k.rev_q15 + 2 * taps_len);
+  h.incr_re = k.incr_re;
+  h.incr_im = k.incr_im;
+  h.qincr_re = k.qincr_re;
+  h.qincr_im = k.qincr_im;
+  h.hist = (long long)taps_len - 1;  // src/xlating.c:552
+  h.zero_before = g->S;
+  h.qzero_before = g->qS;
+  h.is_new = true;
+  xl_client_consts_free(&k);
+  g->dirty = true;
+  *client_id = id;
+  return 0;
+}
+
+extern "C" int xlg_remove_client(xlg_group *g, int client_id) {
+  if (g == nullptr || client_id < 0 || client_id >= (int)g->clients.size() || !g->clients[client_id].active)
+    return -EINVAL;
+  g->clients[client_id].active = false;
+  g->clients[client_id].rev.clear();
+  g->clients[client_id].rev_q15.clear();
+  g->dirty = true;
+  return 0;
+}
+
+extern "C" int xlg_client_count(const xlg_group *g) {
+  if (g == nullptr) return -EINVAL;
+  int n = 0;
+  for (const HostClient &h : g->clients) n += h.active ? 1 : 0;
+  return n;
+}
+
+extern "C" int xlg_client_info(const xlg_group *g, int client_id, size_t *history, int *kernel_kind) {
+  if (g == nullptr || client_id < 0 || client_id >= (int)g->clients.size() || !g->clients[client_id].active)
+    return -EINVAL;
+  if (history) *history = (size_t)g->clients[client_id].hist;
+  if (kernel_kind) *kernel_kind = g->clients[client_id].kind;
+  return 0;
+}
+
+template <int FMT>
+static void launch_convert(bool q15, const void *raw, xlg_group *g, long long S, int n, cudaStream_t st) {
+  const int threads = 256, blocks = (n + threads - 1) / threads;
+  const unsigned mask = (unsigned)(g->ring_cap - 1);
+  if (q15)
+    convert_q15_kernel<FMT><<<blocks, threads, 0, st>>>(raw, g->qring, mask, S, n);
+  else
+    convert_cf32_kernel<FMT><<<blocks, threads, 0, st>>>(raw, g->ring, mask, S, n);
+}
+
+extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t input_len, uint32_t flags) {
+  if (g == nullptr || (input == nullptr && input_len > 0)) return -EINVAL;
+  if (fmt < XLG_FMT_CU8 || fmt > XLG_FMT_CS16) return -EINVAL;
+  if (input_len > g->max_input_len) {
+    XL_LOG("block of %zu elements exceeds max_input_len %u", input_len, g->max_input_len);
+    return -EINVAL;
+  }
+  CU_OK(cudaSetDevice(g->device));
+  const bool q15 = (flags & XLG_PATH_Q15) != 0;
+  const bool dev_in = (flags & XLG_INPUT_DEVICE) != 0;
+  const bool dev_out = (g->flags & XLG_OUT_DEVICE) != 0;
+
+  // clients whose zero-history window has passed may move to the tiled kernel
+  if (!g->dirty && !q15 && g->n_generic > 0 && !(g->flags & XLG_FORCE_GENERIC)) {
+    std::map<std::tuple<uint32_t, size_t, long long>, int> cnt;
+    for (const HostClient &h : g->clients)
+      if (h.active && h.kind == 0 && h.zero_before <= g->S - h.hist) cnt[std::make_tuple(h.D, h.T, h.hist)]++;
+    for (auto &kv : cnt)
+      if (kv.second >= kTileMinClients) {
+        g->dirty = true;
+        break;
+      }
+  }
+  if (q15 && (!g->qring || !g->q_alloc)) {
+    if (drain(g)) return -EIO;
+    int rc = ensure_ring(g, g->hist_cap, true);
+    if (rc) return rc;
+    rc = ensure_arenas(g, g->arena_cap, true);
+    if (rc) return rc;
+  }
+  if (g->dirty) {
+    int rc = rebuild_layout(g);
+    if (rc) return rc;
+  }
+
+  const int64_t ticket = g->next_ticket;
+  Slot &s = g->slots[ticket % XLG_SLOTS];
+  if (s.ticket >= 0) {
+    CU_OK(cudaEventSynchronize(s.ev_done));
+    std::lock_guard<std::mutex> lk(g->mu);
+    harvest_locked(g, s);
+  }
+  const int n = (int)(input_len / 2);  // complex samples (src/xlating.c:387)
+  const long long S = q15 ? g->qS : g->S;
+  const int nc = g->max_client;
+  const unsigned mask = (unsigned)(g->ring_cap - 1);
+
+  // host mirror of the per-client output counts (same integer formula as the
+  // oscillator pre-pass kernel)
+  s.n_out.assign(g->clients.size(), 0);
+  s.out_off.assign(g->clients.size(), 0);
+  s.q15 = q15;
+  s.tile_macs = s.algo_macs = s.out_samples = 0;
+  s.in_samples = (uint64_t)n;
+  int max_generic_out = 0;
+  for (size_t i = 0; i < g->clients.size(); i++) {
+    HostClient &h = g->clients[i];
+    if (!h.active) continue;
+    const long long first = S - h.hist;
+    const long long last_ok = S + n - (long long)h.T;
+    int n_out = 0;
+    if (last_ok >= first) n_out = (int)((last_ok - first) / (long long)h.D) + 1;
+    if (n_out > h.out_cap) n_out = h.out_cap;
+    s.n_out[i] = n_out;
+    s.out_off[i] = h.out_off;
+    h.hist = (S + n) - (first + (long long)n_out * (long long)h.D);
+    s.out_samples += (uint64_t)n_out;
+    s.algo_macs += (uint64_t)n_out * h.T;
+    if (q15 || h.kind == 0) max_generic_out = std::max(max_generic_out, n_out);
+  }
+
+  // ---- input staging ----
+  const void *d_in = input;
+  if (!dev_in && n > 0) {
+    const size_t bytes = (size_t)n * 2 * elem_bytes(fmt);
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, input) == cudaSuccess)
+      pinned = attr.type == cudaMemoryTypeHost;
+    else
+      cudaGetLastError();
+    const void *src = input;
+    if (!pinned) {
+      memcpy(s.h_raw, input, bytes);
+      src = s.h_raw;
+    }
+    CU_OK(cudaMemcpyAsync(s.d_raw, src, bytes, cudaMemcpyHostToDevice, g->s_in));
+    CU_OK(cudaEventRecord(s.ev_h2d, g->s_in));
+    CU_OK(cudaStreamWaitEvent(g->s_c, s.ev_h2d, 0));
+    d_in = s.d_raw;
+  }
+
+  // ---- convert (compute stream) ----
+  s.pf_conv = s.pf_phase = s.pf_tile = s.pf_gen = false;
+  if (n > 0) {
+    if (g->profiling) {
+      CU_OK(cudaEventRecord(s.pf[0], g->s_c));
+      s.pf_conv = true;
+    }
+    if (fmt == XLG_FMT_CU8)
+      launch_convert<0>(q15, d_in, g, S, n, g->s_c);
+    else if (fmt == XLG_FMT_CS8)
+      launch_convert<1>(q15, d_in, g, S, n, g->s_c);
+    else
+      launch_convert<2>(q15, d_in, g, S, n, g->s_c);
+    if (g->profiling) CU_OK(cudaEventRecord(s.pf[1], g->s_c));
+  }
+
+  // ---- oscillator pre-pass (own stream: chains only on the previous pre-pass) ----
+  if (nc > 0) {
+    if (g->profiling) {
+      CU_OK(cudaEventRecord(s.pf[2], g->s_ph));
+      s.pf_phase = true;
+    }
+    const int threads = 64, blocks = (nc + threads - 1) / threads;
+    if (q15)
+      phase_q15_kernel<<<blocks, threads, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk, s.d_qphases, S, n);
+    else
+      phase_cf32_kernel<<<blocks, threads, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk, s.d_phases, S, n);
+    if (g->profiling) CU_OK(cudaEventRecord(s.pf[3], g->s_ph));
+    CU_OK(cudaEventRecord(s.ev_phase, g->s_ph));
+    CU_OK(cudaStreamWaitEvent(g->s_c, s.ev_phase, 0));
+  }
+
+  // ---- FIR ----
+  if (!q15 && !g->classes.empty()) {
+    TileLaunch P;
+    memset(&P, 0, sizeof(P));
+    int ctas = 0;
+    size_t smem = 0;
+    for (TileClassHost &ch : g->classes) {
+      const HostClient &h0 = g->clients[ch.members[0]];
+      const int n_out = s.n_out[ch.members[0]];
+      if (n_out <= 0) continue;
+      TileClass k = ch.k;
+      // hist was already advanced above; recover this block's window start
+      k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
+      k.n_out = n_out;
+      k.tiles = (n_out + T_KT - 1) / T_KT;
+      k.cta_begin = ctas;
+      ctas += k.tiles * k.n_groups;
+      smem = std::max(smem, (size_t)T_SMEM_FIXED + (size_t)k.xs_len * sizeof(float2));
+      P.cls[P.n_classes++] = k;
+      s.tile_macs += (uint64_t)k.tiles * T_KT * (uint64_t)k.L * (uint64_t)ch.members.size();
+    }
+    if (ctas > 0) {
+      if (g->profiling) {
+        CU_OK(cudaEventRecord(s.pf[4], g->s_c));
+        s.pf_tile = true;
+      }
+      fir_tile_cf32_kernel<<<ctas, T_THREADS, smem, g->s_c>>>(P, g->ring, mask, g->d_tile_taps, g->d_members,
+                                                             g->d_clients, s.d_phases, s.d_out);
+      if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], g->s_c));
+    }
+  }
+  if (nc > 0 && max_generic_out > 0) {
+    dim3 grid((max_generic_out + G_OPC - 1) / G_OPC, nc);
+    if (g->profiling) {
+      CU_OK(cudaEventRecord(s.pf[6], g->s_c));
+      s.pf_gen = true;
+    }
+    if (q15)
+      fir_generic_q15_kernel<<<grid, G_THREADS, 0, g->s_c>>>(g->d_clients, s.d_blk, g->qring, mask, g->d_qtaps,
+                                                             s.d_qphases, s.d_qout);
+    else
+      fir_generic_cf32_kernel<<<grid, G_THREADS, 0, g->s_c>>>(g->d_clients, s.d_blk, g->ring, mask, g->d_taps,
+                                                              s.d_phases, s.d_out);
+    if (g->profiling) CU_OK(cudaEventRecord(s.pf[7], g->s_c));
+  }
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaEventRecord(s.ev_fir, g->s_c));
+
+  // ---- results back to the host ----
+  if (!dev_out && g->arena_cap > 0 && nc > 0) {
+    size_t used = 0;
+    for (size_t i = 0; i < g->clients.size(); i++)
+      if (g->clients[i].active) used = std::max(used, (size_t)g->clients[i].out_off + (size_t)s.n_out[i]);
+    CU_OK(cudaStreamWaitEvent(g->s_out, s.ev_fir, 0));
+    if (used > 0) {
+      if (q15)
+        CU_OK(cudaMemcpyAsync(s.h_qout, s.d_qout, used * sizeof(short2), cudaMemcpyDeviceToHost, g->s_out));
+      else
+        CU_OK(cudaMemcpyAsync(s.h_out, s.d_out, used * sizeof(float2), cudaMemcpyDeviceToHost, g->s_out));
+    }
+    CU_OK(cudaEventRecord(s.ev_done, g->s_out));
+  } else {
+    CU_OK(cudaStreamWaitEvent(g->s_out, s.ev_fir, 0));
+    CU_OK(cudaEventRecord(s.ev_done, g->s_out));
+  }
+
+  if (q15)
+    g->qS += n;
+  else
+    g->S += n;
+  s.ticket = ticket;
+  s.harvested = false;
+  g->next_ticket++;
+  return ticket;
+}
+
+extern "C" int xlg_wait(xlg_group *g, int64_t ticket) {
+  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket) return -EINVAL;
+  if (ticket + XLG_SLOTS < g->next_ticket) return -ESTALE;
+  Slot &s = g->slots[ticket % XLG_SLOTS];
+  if (s.ticket != ticket) return -ESTALE;
+  cudaSetDevice(g->device);
+  CU_OK(cudaEventSynchronize(s.ev_done));
+  std::lock_guard<std::mutex> lk(g->mu);
+  harvest_locked(g, s);
+  return 0;
+}
+
+extern "C" int xlg_output(xlg_group *g, int64_t ticket, int client_id, const void **out, size_t *out_len) {
+  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket) return -EINVAL;
+  Slot &s = g->slots[ticket % XLG_SLOTS];
+  if (s.ticket != ticket) return -ESTALE;
+  if (client_id < 0 || client_id >= (int)s.n_out.size()) return -EINVAL;
+  const bool dev_out = (g->flags & XLG_OUT_DEVICE) != 0;
+  if (out_len) *out_len = (size_t)s.n_out[client_id];
+  if (out) {
+    if (s.q15)
+      *out = (dev_out ? s.d_qout : s.h_qout) + s.out_off[client_id];
+    else
+      *out = (dev_out ? s.d_out : s.h_out) + s.out_off[client_id];
+  }
+  return 0;
+}
+
+extern "C" void *xlg_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    XL_LOG("cudaHostAlloc(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void xlg_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+extern "C" int xlg_wait_stream(xlg_group *g, void *cuda_stream) {
+  if (g == nullptr) return -EINVAL;
+  cudaSetDevice(g->device);
+  cudaEvent_t ev;
+  CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU_OK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
+  CU_OK(cudaStreamWaitEvent(g->s_c, ev, 0));
+  CU_OK(cudaStreamWaitEvent(g->s_in, ev, 0));
+  CU_OK(cudaEventDestroy(ev));
+  return 0;
+}
+
+extern "C" int xlg_timer_start(xlg_group *g) {
+  if (g == nullptr) return -EINVAL;
+  cudaSetDevice(g->device);
+  if (drain(g)) return -EIO;
+  CU_OK(cudaEventRecord(g->ev_t0, g->s_c));
+  // every stream starts after t0
+  CU_OK(cudaStreamWaitEvent(g->s_in, g->ev_t0, 0));
+  CU_OK(cudaStreamWaitEvent(g->s_ph, g->ev_t0, 0));
+  CU_OK(cudaStreamWaitEvent(g->s_out, g->ev_t0, 0));
+  return 0;
+}
+
+extern "C" int xlg_timer_stop(xlg_group *g, float *elapsed_ms) {
+  if (g == nullptr || elapsed_ms == nullptr) return -EINVAL;
+  cudaSetDevice(g->device);
+  // s_out's last event already depends on the FIR of the last block; add the others
+  cudaEvent_t ev;
+  CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaStream_t others[] = {g->s_in, g->s_ph, g->s_c};
+  for (cudaStream_t st : others) {
+    CU_OK(cudaEventRecord(ev, st));
+    CU_OK(cudaStreamWaitEvent(g->s_out, ev, 0));
+  }
+  CU_OK(cudaEventRecord(g->ev_t1, g->s_out));
+  CU_OK(cudaEventSynchronize(g->ev_t1));
+  CU_OK(cudaEventDestroy(ev));
+  CU_OK(cudaEventElapsedTime(elapsed_ms, g->ev_t0, g->ev_t1));
+  return 0;
+}
+
+extern "C" int xlg_profile_enable(xlg_group *g, int on) {
+  if (g == nullptr) return -EINVAL;
+  cudaSetDevice(g->device);
+  if (drain(g)) return -EIO;
+  std::lock_guard<std::mutex> lk(g->mu);
+  for (Slot &s : g->slots) harvest_locked(g, s);
+  g->profiling = on != 0;
+  return 0;
+}
+
+extern "C" int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset) {
+  if (g == nullptr || p == nullptr) return -EINVAL;
+  std::lock_guard<std::mutex> lk(g->mu);
+  *p = g->prof;
+  if (reset) memset(&g->prof, 0, sizeof(g->prof));
+  return 0;
+}

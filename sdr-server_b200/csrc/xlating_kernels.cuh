@@ -1,0 +1,545 @@
+/*
+ * csrc/xlating_kernels.cuh -- sm_100a device code of libxlating_b200.
+ *
+ * The hot path of the reference is, per client and per output sample k
+ * (/root/reference/src/xlating.c:52-83):
+ *
+ *     y[k] = phase_k * sum_{j<T} x[first + k*D + j] * rev[j]          (complex, fp32)
+ *
+ * with x the wideband input converted to cf32 (:384-414), rev the reversed
+ * band-pass taps (:525-534) and phase_k a float oscillator advanced once per
+ * output and renormalised once per call (:70-73).  Per input sample and client
+ * this is 4*T/D real FMAs against 8/D output bytes: at the client counts the
+ * service is built for it is bound by the FP32 FMA pipe, not by HBM and not by
+ * tensor cores, so the kernels are organised around
+ * register tiling and shared-memory operand reuse:
+ *
+ *   convert_*        raw cu8/cs8/cs16 block -> cf32 (or Q15) ring in HBM, ONCE per
+ *                    block instead of once per client
+ *   phase_*          the reference's sequential float (or Q15) oscillator, one
+ *                    thread per client, bit-exact (unfused mul/add, exact hypotf)
+ *   fir_tile_cf32    the dominant kernel: 32 clients x 128 outputs per CTA,
+ *                    4 outputs x 8 clients per thread in registers, input tile
+ *                    staged with coalesced 8-byte cp.async into a bank-conflict-
+ *                    free skewed layout, taps streamed by TMA bulk copies
+ *                    (cp.async.bulk + mbarrier, 3 stages)
+ *   fir_generic_*    any (T, D, alignment): one warp per 4 outputs, lanes split the
+ *                    taps, warp-shuffle reduction; also the Q15 integer path
+ *
+ * Everything here is written for sm_100a only.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xl {
+
+// ---------------------------------------------------------------------------
+// device-resident tables
+// ---------------------------------------------------------------------------
+struct ClientDev {
+  long long hist;         // history_offset of the reference (src/xlating.c:29), shared by both paths
+  long long zero_before;  // cf32 ring: samples with absolute index < this read as 0 (attach point)
+  long long qzero_before; // same for the Q15 ring
+  float2 phase;           // oscillator (src/xlating.c:36)
+  float2 incr;            // (src/xlating.c:37)
+  short qph_re, qph_im, qinc_re, qinc_im;  // Q15 oscillator (:39-42)
+  int D;                  // decimation
+  int T;                  // taps_len
+  int taps_off;           // float2 offset of rev taps in the natural arena
+  int qtaps_off;          // short2 offset in the Q15 arena
+  int out_off;            // complex-sample offset in the per-slot output / phase arenas
+  int out_cap;
+  int active;
+  int kind;               // 0 = generic kernel, 1 = tiled kernel
+  int renorm;             // 1 = native behaviour (:73), 0 = AVX behaviour (:336-339)
+  int pad_;
+};
+
+struct BlkInfo {
+  long long first;  // absolute sample index where output 0's window starts
+  int n_out;
+  int pad_;
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul_unfused(float2 a, float2 b) {
+  // two products and one add per component, each rounded (what libgcc's __mulsc3
+  // does for finite operands in the reference's strict build)
+  float2 r;
+  r.x = __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+  r.y = __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+  return r;
+}
+
+__device__ __forceinline__ short sat16(int v) {
+  return (short)max(-32768, min(32767, v));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---------------------------------------------------------------------------
+// convert: raw interleaved I,Q scalars -> ring  (src/xlating.c:389-390, 399-400,
+// 409-410 for cf32; :418, :425, :432 for Q15).  All conversions are exact.
+// ---------------------------------------------------------------------------
+template <int FMT>
+__global__ void convert_cf32_kernel(const void *__restrict__ raw, float2 *__restrict__ ring,
+                                    unsigned mask, long long S, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 v;
+  if (FMT == 0) {
+    uchar2 u = reinterpret_cast<const uchar2 *>(raw)[i];
+    v.x = ((float)u.x - 127.5f) * 0.0078125f;
+    v.y = ((float)u.y - 127.5f) * 0.0078125f;
+  } else if (FMT == 1) {
+    char2 u = reinterpret_cast<const char2 *>(raw)[i];
+    v.x = (float)u.x * 0.0078125f;
+    v.y = (float)u.y * 0.0078125f;
+  } else {
+    short2 u = reinterpret_cast<const short2 *>(raw)[i];
+    v.x = (float)u.x * (1.0f / 32768.0f);
+    v.y = (float)u.y * (1.0f / 32768.0f);
+  }
+  ring[(unsigned)((unsigned long long)(S + i)) & mask] = v;
+}
+
+template <int FMT>
+__global__ void convert_q15_kernel(const void *__restrict__ raw, short2 *__restrict__ ring,
+                                   unsigned mask, long long S, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  short2 v;
+  if (FMT == 0) {
+    uchar2 u = reinterpret_cast<const uchar2 *>(raw)[i];
+    v.x = (short)(((int)u.x - 128) << 8);
+    v.y = (short)(((int)u.y - 128) << 8);
+  } else if (FMT == 1) {
+    char2 u = reinterpret_cast<const char2 *>(raw)[i];
+    v.x = (short)((int)u.x << 8);
+    v.y = (short)((int)u.y << 8);
+  } else {
+    v = reinterpret_cast<const short2 *>(raw)[i];
+  }
+  ring[(unsigned)((unsigned long long)(S + i)) & mask] = v;
+}
+
+// ---------------------------------------------------------------------------
+// oscillator pre-pass.  The phase sequence does not depend on the data, only on
+// how many outputs each call produces, so it is computed apart from the FIR --
+// but it cannot be parallelised or put in closed form: parity is against the
+// reference's float recursion, which drifts 4e-3 rad per block
+// from exact math.  One thread per client replays it bit for bit and stores the
+// phase of every output of this block.
+// ---------------------------------------------------------------------------
+__global__ void phase_cf32_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
+                                  float2 *__restrict__ phases, long long S, int n_in) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clients) return;
+  ClientDev *d = cl + c;
+  if (!d->active) return;
+  const long long first = S - d->hist;
+  const long long last_ok = S + n_in - d->T;  // last admissible window start (src/xlating.c:58-60)
+  int n_out = 0;
+  if (last_ok >= first) n_out = (int)((last_ok - first) / d->D) + 1;
+  if (n_out > d->out_cap) n_out = d->out_cap;  // cannot happen for input_len <= max_input_len
+  BlkInfo b;
+  b.first = first;
+  b.n_out = n_out;
+  b.pad_ = 0;
+  blk[c] = b;
+  float2 p = d->phase;
+  const float2 inc = d->incr;
+  float2 *row = phases + d->out_off;
+  for (int k = 0; k < n_out; k++) {
+    row[k] = p;
+    p = cmul_unfused(p, inc);  // src/xlating.c:71
+  }
+  if (n_out > 0 && d->renorm) {
+    // src/xlating.c:73.  glibc's hypotf is (float)sqrt((double)x*x + (double)y*y)
+    // (verified on 5e7 random inputs); the products are exact in double.
+    const double m2 = (double)p.x * (double)p.x + (double)p.y * (double)p.y;
+    const float mag = (float)sqrt(m2);
+    p.x = __fdiv_rn(p.x, mag);
+    p.y = __fdiv_rn(p.y, mag);
+  }
+  d->phase = p;
+  d->hist = (S + n_in) - (first + (long long)n_out * d->D);  // src/xlating.c:76
+}
+
+__global__ void phase_q15_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
+                                 short2 *__restrict__ qphases, long long S, int n_in) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clients) return;
+  ClientDev *d = cl + c;
+  if (!d->active) return;
+  const long long first = S - d->hist;
+  const long long last_ok = S + n_in - d->T;
+  int n_out = 0;
+  if (last_ok >= first) n_out = (int)((last_ok - first) / d->D) + 1;
+  if (n_out > d->out_cap) n_out = d->out_cap;
+  BlkInfo b;
+  b.first = first;
+  b.n_out = n_out;
+  b.pad_ = 0;
+  blk[c] = b;
+  int pr = d->qph_re, pi = d->qph_im;
+  const int ir = d->qinc_re, ii = d->qinc_im;
+  short2 *row = qphases + d->out_off;
+  for (int k = 0; k < n_out; k++) {
+    row[k] = make_short2((short)pr, (short)pi);
+    const int nr = pr * ir - pi * ii;  // src/xlating.c:126-129 (no renormalisation)
+    const int ni = pr * ii + pi * ir;
+    pr = sat16(nr >> 15);
+    pi = sat16(ni >> 15);
+  }
+  d->qph_re = (short)pr;
+  d->qph_im = (short)pi;
+  d->hist = (S + n_in) - (first + (long long)n_out * d->D);  // src/xlating.c:133
+}
+
+// ---------------------------------------------------------------------------
+// generic FIR: any T, D, alignment, attach point.  CTA = 8 warps = 32 consecutive
+// outputs of one client; each warp owns 4 consecutive outputs, its lanes stride
+// over the taps (coalesced float2 loads of ring and taps through L1/L2) and the
+// partial dot products are combined with warp shuffles.
+// ---------------------------------------------------------------------------
+constexpr int G_THREADS = 256;
+constexpr int G_OPW = 4;                       // outputs per warp
+constexpr int G_OPC = (G_THREADS / 32) * G_OPW;  // outputs per CTA
+
+__global__ void __launch_bounds__(G_THREADS)
+fir_generic_cf32_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restrict__ blk,
+                        const float2 *__restrict__ ring, unsigned mask,
+                        const float2 *__restrict__ taps, const float2 *__restrict__ phases,
+                        float2 *__restrict__ out) {
+  const int c = blockIdx.y;
+  const ClientDev *d = cl + c;
+  if (!d->active || d->kind != 0) return;
+  const BlkInfo b = blk[c];
+  const int kbase = blockIdx.x * G_OPC;
+  if (kbase >= b.n_out) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = kbase + warp * G_OPW;
+  const int T = d->T, D = d->D;
+  const long long zb = d->zero_before;
+  const float2 *tp = taps + d->taps_off;
+
+  float2 acc[G_OPW];
+#pragma unroll
+  for (int i = 0; i < G_OPW; i++) acc[i] = make_float2(0.f, 0.f);
+
+  const long long w0 = b.first + (long long)k0 * D;
+  for (int j = lane; j < T; j += 32) {
+    const float2 t = __ldg(tp + j);
+#pragma unroll
+    for (int i = 0; i < G_OPW; i++) {
+      const long long ab = w0 + (long long)i * D + j;
+      float2 x = make_float2(0.f, 0.f);
+      if (ab >= zb) x = ring[(unsigned)((unsigned long long)ab) & mask];
+      acc[i].x = fmaf(x.x, t.x, acc[i].x);
+      acc[i].x = fmaf(-x.y, t.y, acc[i].x);
+      acc[i].y = fmaf(x.x, t.y, acc[i].y);
+      acc[i].y = fmaf(x.y, t.x, acc[i].y);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < G_OPW; i++) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, s);
+      acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, s);
+    }
+  }
+  // lane i finishes output i (every lane holds all four sums after the butterfly)
+  float2 mine = acc[0];
+#pragma unroll
+  for (int i = 1; i < G_OPW; i++)
+    if (lane == i) mine = acc[i];
+  const int k = k0 + lane;
+  if (lane < G_OPW && k < b.n_out) {
+    const float2 ph = phases[d->out_off + k];
+    out[d->out_off + k] = cmul_unfused(mine, ph);  // src/xlating.c:70
+  }
+}
+
+// Q15 integer path (src/xlating.c:92-140): int16 x int16 products accumulated in
+// int64 -- integer addition is associative, so the lane-split + shuffle reduction
+// is bit-exact against the reference's sequential loop.
+__global__ void __launch_bounds__(G_THREADS)
+fir_generic_q15_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restrict__ blk,
+                       const short2 *__restrict__ ring, unsigned mask,
+                       const short2 *__restrict__ qtaps, const short2 *__restrict__ qphases,
+                       short2 *__restrict__ out) {
+  const int c = blockIdx.y;
+  const ClientDev *d = cl + c;
+  if (!d->active) return;
+  const BlkInfo b = blk[c];
+  const int kbase = blockIdx.x * G_OPC;
+  if (kbase >= b.n_out) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = kbase + warp * G_OPW;
+  const int T = d->T, D = d->D;
+  const long long zb = d->qzero_before;
+  const short2 *tp = qtaps + d->qtaps_off;
+
+  long long are[G_OPW], aim[G_OPW];
+#pragma unroll
+  for (int i = 0; i < G_OPW; i++) are[i] = aim[i] = 0;
+
+  const long long w0 = b.first + (long long)k0 * D;
+  for (int j = lane; j < T; j += 32) {
+    const short2 t = __ldg(tp + j);
+#pragma unroll
+    for (int i = 0; i < G_OPW; i++) {
+      const long long ab = w0 + (long long)i * D + j;
+      short2 x = make_short2(0, 0);
+      if (ab >= zb) x = ring[(unsigned)((unsigned long long)ab) & mask];
+      are[i] += (long long)((int)x.x * (int)t.x) - (long long)((int)x.y * (int)t.y);  // :114
+      aim[i] += (long long)((int)x.x * (int)t.y) + (long long)((int)x.y * (int)t.x);  // :115
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < G_OPW; i++) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      are[i] += __shfl_xor_sync(0xffffffffu, are[i], s);
+      aim[i] += __shfl_xor_sync(0xffffffffu, aim[i], s);
+    }
+  }
+  long long mre = are[0], mim = aim[0];
+#pragma unroll
+  for (int i = 1; i < G_OPW; i++)
+    if (lane == i) {
+      mre = are[i];
+      mim = aim[i];
+    }
+  const int k = k0 + lane;
+  if (lane < G_OPW && k < b.n_out) {
+    const int ar = sat16((int)(mre >> 15));  // :118-119
+    const int ai = sat16((int)(mim >> 15));
+    const short2 ph = qphases[d->out_off + k];
+    const int rr = ar * (int)ph.x - ai * (int)ph.y;  // :121-122
+    const int ri = ar * (int)ph.y + ai * (int)ph.x;
+    out[d->out_off + k] = make_short2(sat16(rr >> 15), sat16(ri >> 15));  // :123-124
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tiled multi-client FIR (the dominant kernel)
+// ---------------------------------------------------------------------------
+constexpr int T_THREADS = 128;
+constexpr int T_WARPS = T_THREADS / 32;
+constexpr int T_RK = 4;              // outputs per thread (k = k0 + lane + 32*i)
+constexpr int T_RC = 8;              // clients per thread
+constexpr int T_KT = 32 * T_RK;      // 128 outputs per CTA
+constexpr int T_CG = T_WARPS * T_RC; // 32 clients per CTA
+constexpr int T_JC = 32;             // flat taps per TMA chunk
+constexpr int T_STAGES = 3;
+constexpr int T_CHUNK_F2 = T_JC * T_CG;       // float2 per chunk (1024)
+constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
+constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
+constexpr int T_MAX_CLASSES = 8;
+
+// One class = clients with identical (D, T, window alignment).  "Flat" tap index:
+// tap j = q*D + r lives at f = q*Dp + r with Dp = D rounded up to odd, so that a
+// thread's window x[(k*D + j)] sits at shared address k*Dp + f: consecutive f for
+// the inner loop (immediate offsets when unrolled) and an odd stride between the
+// lanes' outputs (conflict-free 64-bit shared loads).  Pad slots hold zero taps.
+struct TileClass {
+  long long first;     // absolute index of output 0's window start (all members)
+  long long taps_off;  // float2 offset into the packed tile-tap arena: [group][L][32]
+  int n_out;
+  int D, Dp, L;        // L = flat length, multiple of 8
+  int n_groups;        // CTA groups of 32 clients
+  int tiles;           // ceil(n_out / 128)
+  int cta_begin;       // first CTA of this class in the launch
+  int members_off;     // into the members table: client index or -1, 32 per group
+  int xs_len;          // float2 in the input tile: (T_KT-1)*Dp + L
+  int pad_;
+};
+
+struct TileLaunch {
+  int n_classes;
+  int pad_;
+  TileClass cls[T_MAX_CLASSES];
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(T_THREADS)
+fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
+                     const float2 *__restrict__ tile_taps, const int *__restrict__ members,
+                     const ClientDev *__restrict__ cl, const float2 *__restrict__ phases,
+                     float2 *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2 *ts = reinterpret_cast<float2 *>(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + T_STAGES * T_CHUNK_BYTES);
+  float2 *xs = reinterpret_cast<float2 *>(smem + T_SMEM_FIXED);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // which class / client group / output tile is this CTA?
+  int ci = 0;
+  while (ci + 1 < P.n_classes && (int)blockIdx.x >= P.cls[ci + 1].cta_begin) ci++;
+  const TileClass &K = P.cls[ci];
+  const int local = (int)blockIdx.x - K.cta_begin;
+  const int grp = local / K.tiles;
+  const int tile = local - grp * K.tiles;
+  const int k0 = tile * T_KT;
+  const int D = K.D, Dp = K.Dp, L = K.L;
+  const int nchunks = (L + T_JC - 1) / T_JC;
+
+  if (tid == 0) {
+    for (int s = 0; s < T_STAGES; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const float2 *gt = tile_taps + K.taps_off + (long long)grp * L * T_CG;
+  if (tid == 0) {
+    for (int s = 0; s < T_STAGES && s < nchunks; s++) {
+      const unsigned bytes = (unsigned)min(T_JC, L - s * T_JC) * T_CG * 8u;
+      mbar_expect_tx(&bars[s], bytes);
+      tma_bulk_g2s(ts + s * T_CHUNK_F2, gt + (long long)s * T_CHUNK_F2, bytes, &bars[s]);
+    }
+  }
+
+  // stage the input tile: row r of the tile = D consecutive stream samples, stored
+  // with pitch Dp.  Consecutive threads read consecutive float2 (coalesced).
+  {
+    const long long w0 = K.first + (long long)k0 * D;
+    int row = tid / Dp, col = tid - row * Dp;
+    const int drow = T_THREADS / Dp, dcol = T_THREADS - drow * Dp;
+    for (int e = tid; e < K.xs_len; e += T_THREADS) {
+      if (col < D) {
+        const long long ab = w0 + (long long)row * D + col;
+        cp_async_8(xs + e, ring + ((unsigned)((unsigned long long)ab) & mask));
+      } else {
+        xs[e] = make_float2(0.f, 0.f);
+      }
+      row += drow;
+      col += dcol;
+      if (col >= Dp) {
+        col -= Dp;
+        row++;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int *mem = members + K.members_off + grp * T_CG + warp * T_RC;
+  const bool warp_active = mem[0] >= 0;  // members are packed from the front of a group
+
+  float2 acc[T_RK][T_RC];
+#pragma unroll
+  for (int i = 0; i < T_RK; i++)
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+
+  const float2 *xb0 = xs + lane * Dp;
+  const float2 *xb1 = xb0 + 32 * Dp;
+  const float2 *xb2 = xb1 + 32 * Dp;
+  const float2 *xb3 = xb2 + 32 * Dp;
+
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int s = ch % T_STAGES;
+    mbar_wait(&bars[s], (unsigned)((ch / T_STAGES) & 1));
+    if (warp_active) {
+      const int len = min(T_JC, L - ch * T_JC);
+      const float4 *tp = reinterpret_cast<const float4 *>(ts + s * T_CHUNK_F2 + warp * T_RC);
+      const int fbase = ch * T_JC;
+      for (int f = 0; f < len; f += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          float2 x[T_RK];
+          x[0] = xb0[fbase + f + u];
+          x[1] = xb1[fbase + f + u];
+          x[2] = xb2[fbase + f + u];
+          x[3] = xb3[fbase + f + u];
+          float4 tq[T_RC / 2];
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+          for (int i = 0; i < T_RK; i++) {
+#pragma unroll
+            for (int q = 0; q < T_RC / 2; q++) {
+              float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+              a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+              a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+              a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+              a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+              a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+              a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+              a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+              a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with stage s
+    if (tid == 0 && ch + T_STAGES < nchunks) {
+      const int nx = ch + T_STAGES;
+      const unsigned bytes = (unsigned)min(T_JC, L - nx * T_JC) * T_CG * 8u;
+      mbar_expect_tx(&bars[s], bytes);
+      tma_bulk_g2s(ts + s * T_CHUNK_F2, gt + (long long)nx * T_CHUNK_F2, bytes, &bars[s]);
+    }
+  }
+
+  // epilogue: derotate with the pre-computed oscillator and store (coalesced in k)
+  if (warp_active) {
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) {
+      const int m = mem[c];
+      if (m < 0) continue;
+      const int off = cl[m].out_off;
+#pragma unroll
+      for (int i = 0; i < T_RK; i++) {
+        const int k = k0 + lane + 32 * i;
+        if (k < K.n_out) {
+          const float2 ph = phases[off + k];
+          out[off + k] = cmul_unfused(acc[i][c], ph);  // src/xlating.c:70
+        }
+      }
+    }
+  }
+}
+
+}  // namespace xl

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle.
+
+* the reference's own known-answer fixtures (tests/golden/reference_fixtures.json)
+  with the reference's own assert semantics (test/utils.c:176-196);
+* seeded random streams vs oracle/liboracle.so: float path within the contract's
+  tolerance (tests/util.py: norm-wise 1e-5 and element-wise 1e-5*|ref| +
+  1e-5*max|ref|), Q15 path bit-exact;
+* the reference's edge cases: too-short input -> 0 outputs (test_xlating.c:63-81),
+  ragged call sizes, state carry-over, even tap counts, mid-stream attach.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from util import assert_cf32_close, ramp, rand_block, trunc4
+
+pytestmark = pytest.mark.gpu
+
+
+def fixture_filter(pkg, fixtures, max_input):
+    s = fixtures["xlating"]["setup"]
+    taps = pkg.create_low_pass_filter(s["lpf"]["gain"], s["sampling_freq"], s["lpf"]["cutoff"],
+                                      s["lpf"]["transition_width"])
+    assert len(taps) == s["ntaps"]
+    return pkg.XlatingFilter(s["decimation"], taps, s["center_freq"], s["sampling_freq"], max_input)
+
+
+def assert_golden_cf32(y, expected):
+    """Reference semantics: (int32)(x*10000) equality.  The truncation is brittle
+    within float noise of a multiple of 1e-4, so a mismatch is accepted only if the
+    values agree to 1e-6 absolute (never needed so far)."""
+    exp = np.asarray(expected, dtype=np.float32)
+    got = np.asarray(y).view(np.float32)
+    assert got.shape == exp.shape
+    bad = np.nonzero(trunc4(got) != trunc4(exp))[0]
+    for i in bad:
+        assert abs(float(got[i]) - float(exp[i])) <= 1e-6, (i, got[i], exp[i])
+
+
+# ---------------------------------------------------------------------------
+# reference fixtures through the drop-in ABI
+# ---------------------------------------------------------------------------
+def test_fixture_full_block(pkg, fixtures):
+    """test/test_xlating.c:24-37"""
+    g = fixtures["xlating"]["max_input_buffer_size"]
+    f = fixture_filter(pkg, fixtures, g["max_input"])
+    x = ramp("cu8", 0, g["input_len"])
+    y = f.process_cf32("cu8", x)
+    assert len(y) == len(g["cf32"]) // 2
+    assert_golden_cf32(y, g["cf32"])
+    q = f.process_q15("cu8", x)
+    np.testing.assert_array_equal(q.reshape(-1), np.array(g["cs16"], dtype=np.int16))
+    f.close()
+
+
+def test_fixture_partial_blocks(pkg, fixtures):
+    """test/test_xlating.c:39-61 -- history and phase carry over between calls"""
+    g = fixtures["xlating"]["partial_input_buffer_size"]
+    f = fixture_filter(pkg, fixtures, g["max_input"])
+    x0 = ramp("cu8", 0, g["input_len"])
+    assert_golden_cf32(f.process_cf32("cu8", x0), g["cf32"])
+    np.testing.assert_array_equal(f.process_q15("cu8", x0).reshape(-1), np.array(g["cs16"], dtype=np.int16))
+    x1 = ramp("cu8", 200, g["input_len"])
+    assert_golden_cf32(f.process_cf32("cu8", x1), g["next_cf32"])
+    np.testing.assert_array_equal(f.process_q15("cu8", x1).reshape(-1), np.array(g["next_cs16"], dtype=np.int16))
+    f.close()
+
+
+def test_fixture_small_input(pkg, fixtures):
+    """test/test_xlating.c:63-81 -- not enough data for an output"""
+    g = fixtures["xlating"]["small_input_data"]
+    f = fixture_filter(pkg, fixtures, g["max_input"])
+    x = ramp("cu8", 0, g["first_len"])
+    assert len(f.process_cf32("cu8", x)) == 20
+    assert len(f.process_q15("cu8", x)) == 20
+    x = ramp("cu8", 200, g["second_len"])
+    assert len(f.process_cf32("cu8", x)) == g["expected_outputs"]
+    assert len(f.process_q15("cu8", x)) == g["expected_outputs"]
+    f.close()
+
+
+@pytest.mark.parametrize("fmt,key", [("cu8", "rtlsdr_cu8"), ("cs16", "airspy_cs16"), ("cs8", "hackrf_cs8")])
+def test_fixture_tcp_server(pkg, fixtures, fmt, key):
+    """test/test_tcp_server.c:154-248: dsp_worker_start's filter on the mock SDR ramps"""
+    s = fixtures["tcp_server"]["setup"]
+    taps = pkg.create_low_pass_filter(1.0, s["band_sampling_rate"], s["lpf"]["cutoff"], s["lpf"]["transition_width"])
+    f = pkg.XlatingFilter(s["decimation"], taps, s["center_offset"], s["band_sampling_rate"], s["buffer_size"])
+    y = f.process_cf32(fmt, ramp(fmt, 0, s["input_elements"]))
+    assert len(y) == len(fixtures["tcp_server"][key]) // 2
+    assert_golden_cf32(y, fixtures["tcp_server"][key])
+    f.close()
+
+
+# ---------------------------------------------------------------------------
+# drop-in ABI vs oracle on random streams
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["native", "optimized"])
+@pytest.mark.parametrize("fmt", ["cu8", "cs8", "cs16"])
+@pytest.mark.parametrize("fs,rate,tw,center", [(48000, 9600, 2000, -12000), (2016000, 48000, 16400, -312000),
+                                               (2016000, 96000, 19200, 400123), (10000000, 250000, 50000, 1234567)])
+def test_dropin_stream_vs_oracle(pkg, fmt, variant, fs, rate, tw, center):
+    rng = np.random.default_rng(99)
+    taps = pkg.create_low_pass_filter(1.0, fs, rate // 2, tw)
+    D = fs // rate
+    max_in = 40000
+    f = pkg.XlatingFilter(D, taps, center, fs, max_in)
+    o = po.OracleFilter(D, taps, center, fs, max_in)
+    fq = pkg.XlatingFilter(D, taps, center, fs, max_in)
+    oq = po.OracleFilter(D, taps, center, fs, max_in)
+    for n in [40000, 2, 38, 12346, 0, 40000, 20000, 4, 39998, 40000]:
+        x = rand_block(rng, fmt, n)
+        assert_cf32_close(f.process_cf32(fmt, x, variant), o.process_cf32(fmt, x), f"{fmt} n={n}")
+        np.testing.assert_array_equal(fq.process_q15(fmt, x, variant), oq.process_q15(fmt, x))
+    f.close()
+    fq.close()
+
+
+def test_dropin_even_taps_and_tiny_filter(pkg):
+    """even tap counts keep the reference's reversal quirk; T=1 and D=1 edge cases"""
+    rng = np.random.default_rng(5)
+    for T, D in [(8, 2), (1, 1), (2, 3), (33, 1), (64, 7)]:
+        taps = rng.standard_normal(T).astype(np.float32) * 0.2
+        f = pkg.XlatingFilter(D, taps, 1000, 48000, 4096)
+        o = po.OracleFilter(D, taps, 1000, 48000, 4096)
+        for n in [4096, 10, 4096, 1024]:
+            x = rand_block(rng, "cu8", n)
+            assert_cf32_close(f.process_cf32("cu8", x), o.process_cf32("cu8", x), f"T={T} D={D} n={n}")
+        f.close()
+
+
+def test_dropin_long_stream_phase_drift(pkg):
+    """300 consecutive full blocks: a closed-form oscillator would exceed 1e-5 by
+    block ~10; the replayed float recursion must not drift."""
+    rng = np.random.default_rng(7)
+    fs, rate = 2016000, 48000
+    taps = pkg.create_low_pass_filter(1.0, fs, rate // 2, 16400)
+    f = pkg.XlatingFilter(fs // rate, taps, -312000, fs, 65536)
+    o = po.OracleFilter(fs // rate, taps, -312000, fs, 65536)
+    worst = 0.0
+    for b in range(300):
+        x = rand_block(rng, "cu8", 65536)
+        worst = max(worst, assert_cf32_close(f.process_cf32("cu8", x), o.process_cf32("cu8", x), f"block {b}"))
+    assert worst < 1e-5
+    f.close()
+
+
+# ---------------------------------------------------------------------------
+# batch ABI
+# ---------------------------------------------------------------------------
+def make_group(pkg, fs, max_in, plan, flags=0):
+    g = pkg.Group(fs, max_in, flags=flags)
+    oracles, ids = [], []
+    for p in plan:
+        taps = pkg.create_low_pass_filter(1.0, fs, p["cutoff"], p["tw"])
+        ids.append(g.add_client(p["decimation"], taps, p["center"]))
+        oracles.append(po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in))
+    return g, ids, oracles
+
+
+@pytest.mark.parametrize("flags", [0, 4])  # 4 = XLG_FORCE_GENERIC
+@pytest.mark.parametrize("fmt", ["cu8", "cs16"])
+def test_group_mixed_clients_vs_oracle(pkg, fmt, flags):
+    """40 clients, mixed 48/96 ksps (two tiled classes of 20 each) + 3 odd ones
+    (generic kernel) on one shared input, several ragged blocks."""
+    rng = np.random.default_rng(11)
+    fs, max_in = 2016000, 65536
+    plan = pkg.client_plan(fs, [48000 if c % 2 == 0 else 96000 for c in range(40)], tw=None)
+    plan += [{"rate": 252000, "decimation": 8, "center": 100000, "cutoff": 100000, "tw": 60000},
+             {"rate": 48000, "decimation": 42, "center": -5000, "cutoff": 24000, "tw": 16400},
+             {"rate": 16000, "decimation": 126, "center": 777777, "cutoff": 8000, "tw": 3200}]
+    g, ids, oracles = make_group(pkg, fs, max_in, plan, flags)
+    kinds = set()
+    for blk, n in enumerate([65536, 65536, 30000, 2, 65536, 12346, 65536]):
+        x = rand_block(rng, fmt, n)
+        t = g.submit(fmt, x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32(fmt, x), f"block {blk} client {cid}")
+            assert g.client_info(cid)[0] == o.history
+        kinds |= {g.client_info(cid)[1] for cid in ids}
+    assert kinds == ({0} if flags else {0, 1})
+    g.close()
+
+
+def test_group_pipelined_tickets(pkg):
+    """XLG_SLOTS blocks in flight before the first wait; outputs stay valid."""
+    rng = np.random.default_rng(13)
+    fs, max_in = 2016000, 32768
+    plan = pkg.client_plan(fs, [48000] * 16, tw=16400)
+    g, ids, oracles = make_group(pkg, fs, max_in, plan)
+    blocks = [rand_block(rng, "cu8", max_in) for _ in range(12)]
+    refs = [[o.process_cf32("cu8", x) for o in oracles] for x in blocks]
+    pending = []
+    for b, x in enumerate(blocks):
+        pending.append((b, g.submit("cu8", x)))
+        if len(pending) == pkg.XLG_SLOTS:
+            bb, t = pending.pop(0)
+            g.wait(t)
+            for cid, r in zip(ids, refs[bb]):
+                assert_cf32_close(g.output(t, cid), r, f"block {bb} client {cid}")
+    for bb, t in pending:
+        g.wait(t)
+        for cid, r in zip(ids, refs[bb]):
+            assert_cf32_close(g.output(t, cid), r, f"block {bb} client {cid}")
+    g.close()
+
+
+def test_group_attach_and_detach_midstream(pkg):
+    """A client added at stream position P behaves like a reference filter created
+    at that moment (zero history, phase 1): src/xlating.c:543-565."""
+    rng = np.random.default_rng(17)
+    fs, max_in = 2016000, 32768
+    plan = pkg.client_plan(fs, [48000] * 12, tw=16400)
+    g, ids, oracles = make_group(pkg, fs, max_in, plan)
+    for _ in range(3):
+        x = rand_block(rng, "cu8", max_in)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x))
+    # attach 10 more (one aligned class of its own) + 1 loner, detach two
+    late = pkg.client_plan(fs, [96000] * 10, tw=19200) + [
+        {"rate": 48000, "decimation": 42, "center": 1234, "cutoff": 24000, "tw": 9600}]
+    for p in late:
+        taps = pkg.create_low_pass_filter(1.0, fs, p["cutoff"], p["tw"])
+        ids.append(g.add_client(p["decimation"], taps, p["center"]))
+        oracles.append(po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in))
+    for victim in (ids[1], ids[5]):
+        g.remove_client(victim)
+    keep = [(c, o) for c, o in zip(ids, oracles) if c not in (ids[1], ids[5])]
+    assert g.client_count() == len(keep)
+    for blk in range(5):
+        n = max_in if blk != 2 else 1000
+        x = rand_block(rng, "cu8", n)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for cid, o in keep:
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"block {blk} client {cid}")
+    g.close()
+
+
+def test_group_q15_path_bit_exact(pkg):
+    rng = np.random.default_rng(19)
+    fs, max_in = 2016000, 32768
+    plan = pkg.client_plan(fs, [48000, 96000, 48000, 96000], tw=None)
+    g, ids, oracles = make_group(pkg, fs, max_in, plan)
+    for n in [max_in, 500, max_in]:
+        x = rand_block(rng, "cs16", n)
+        t = g.submit("cs16", x, flags=pkg.XLG_PATH_Q15)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            np.testing.assert_array_equal(g.output(t, cid, q15=True), o.process_q15("cs16", x))
+    g.close()
+
+
+def test_group_full_size_cfg2_sampled(pkg):
+    """BASELINE configs[1] at full size: 256 clients, mixed 48/96 ksps, 262144-byte
+    cu8 blocks; 8 sampled clients are checked against the oracle on 3 blocks, all
+    clients' output counts on every block."""
+    rng = np.random.default_rng(23)
+    fs, max_in = 2016000, 262144
+    plan = pkg.client_plan(fs, [48000 if c % 2 == 0 else 96000 for c in range(256)], tw=None)
+    g = pkg.Group(fs, max_in)
+    ids = []
+    tapsets = {}
+    for p in plan:
+        key = (p["cutoff"], p["tw"])
+        if key not in tapsets:
+            tapsets[key] = pkg.create_low_pass_filter(1.0, fs, p["cutoff"], p["tw"])
+        ids.append(g.add_client(p["decimation"], tapsets[key], p["center"]))
+    sample = [0, 1, 2, 101, 128, 200, 254, 255]
+    oracles = {c: po.OracleFilter(plan[c]["decimation"], tapsets[(plan[c]["cutoff"], plan[c]["tw"])],
+                                  plan[c]["center"], fs, max_in) for c in sample}
+    for blk in range(3):
+        x = rand_block(rng, "cu8", max_in)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for c in sample:
+            assert_cf32_close(g.output(t, ids[c]), oracles[c].process_cf32("cu8", x), f"block {blk} client {c}")
+        counts = [g.output_ptr(t, cid)[1] for cid in ids]
+        assert all(n in (3120, 3121, 3122) for n in counts[0::2]) and all(n in (6241, 6242, 6243) for n in counts[1::2])
+    assert all(g.client_info(cid)[1] == 1 for cid in ids)  # all on the tiled kernel
+    g.close()
+
+
+def test_group_linearity_full_size(pkg):
+    """Size-independent property at full size: the filter is linear in the input
+    samples around the converter's zero level, so y(a) + y(b) - y(zero level) ==
+    y(a + b - zero) for cs16 inputs (exact integers, so only float rounding of the
+    sums differs)."""
+    rng = np.random.default_rng(29)
+    fs, max_in = 2016000, 262144
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 16400)
+    plan = pkg.client_plan(fs, [48000] * 64, tw=16400)
+    outs = []
+    a = rng.integers(-8000, 8000, max_in, dtype=np.int16)
+    b = rng.integers(-8000, 8000, max_in, dtype=np.int16)
+    for x in (a, b, (a + b).astype(np.int16)):
+        g = pkg.Group(fs, max_in)
+        ids = [g.add_client(p["decimation"], taps, p["center"]) for p in plan]
+        t = g.submit("cs16", x)
+        g.wait(t)
+        outs.append(np.stack([g.output(t, c) for c in ids]))
+        g.close()
+    ya, yb, yab = outs
+    err = np.max(np.abs((ya + yb) - yab)) / np.max(np.abs(yab))
+    assert err < 5e-6, err
