@@ -116,9 +116,11 @@ def test_dropin_stream_vs_oracle(pkg, fmt, variant, fs, rate, tw, center):
 
 
 def test_dropin_even_taps_and_tiny_filter(pkg):
-    """even tap counts keep the reference's reversal quirk; T=1 and D=1 edge cases"""
+    """even tap counts keep the reference's reversal quirk; T=1 and D=1 edge cases.
+    (D > T is excluded: there the reference's history_offset underflows,
+    src/xlating.c:76 -- undefined behaviour, so there is nothing to be on par with.)"""
     rng = np.random.default_rng(5)
-    for T, D in [(8, 2), (1, 1), (2, 3), (33, 1), (64, 7)]:
+    for T, D in [(8, 2), (1, 1), (4, 3), (33, 1), (64, 7)]:
         taps = rng.standard_normal(T).astype(np.float32) * 0.2
         f = pkg.XlatingFilter(D, taps, 1000, 48000, 4096)
         o = po.OracleFilter(D, taps, 1000, 48000, 4096)
@@ -284,10 +286,9 @@ def test_group_full_size_cfg2_sampled(pkg):
 
 
 def test_group_linearity_full_size(pkg):
-    """Size-independent property at full size: the filter is linear in the input
-    samples around the converter's zero level, so y(a) + y(b) - y(zero level) ==
-    y(a + b - zero) for cs16 inputs (exact integers, so only float rounding of the
-    sums differs)."""
+    """Size-independent property at full size: the cs16 converter has no offset
+    (x/32768, src/xlating.c:409-410), so the whole path is linear in the input:
+    y(a) + y(b) == y(a + b) up to float rounding of the sums."""
     rng = np.random.default_rng(29)
     fs, max_in = 2016000, 262144
     taps = pkg.create_low_pass_filter(1.0, fs, 24000, 16400)
