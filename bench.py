@@ -1,0 +1,428 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the xlating FIR decimator hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload cfg2|cfg1|cfg3|c1000] [--taps default|297]
+
+A "step" is one pass of the hot path over one block of the wideband stream:
+convert once, then NCO-mix + FIR + decimate for ALL clients (one fused launch).
+Default workload = BASELINE.json configs[1]: 256 clients on one shared 2.016 Msps
+cu8 stream, mixed 48/96 ksps, 262144-byte blocks (the reference's default
+buffer_size, src/config.c:208), taps from the server's own designer
+(src/dsp_worker.c:98 with lpf_cutoff_rate=5 -> 505 / 253 taps).
+
+The JSON line (rank 0):
+  value      input MS/s, whole job (all N GPUs; each GPU decimates its own
+             independent stream: weak scaling, no collective on the data path),
+             inputs resident in HBM, timed on the device with CUDA events, max over ranks
+  e2e        same metric through the C ABI with HOST buffers: pinned H2D of every
+             block and D2H of every client's output inside the timed region
+  roofline   the dominant kernel (fir_tile_cf32_kernel) against the HBM roofline the
+             metric names, plus "fp32": the FP32-FMA roofline that actually binds
+  cpu_baseline  the reference's own CPU path (oracle/_ref, compiled from the
+             unmodified reference sources) on this box's host cores, thread-per-client
+
+--impl reference prints the CPU arm alone (same metric/config).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BLOCK_BYTES = 262144  # src/config.c:208
+
+
+# ---------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------
+def workload(name, taps_mode):
+    if name == "cfg2":
+        fs, fmt, rates = 2016000, "cu8", [48000 if c % 2 == 0 else 96000 for c in range(256)]
+        desc = "cfg2: 256 clients, shared 2.016 Msps cu8 input, mixed 48/96 ksps"
+    elif name == "cfg1":
+        fs, fmt, rates = 2016000, "cu8", [48000]
+        desc = "cfg1: 1 client, 2.016 Msps cu8 -> 48 ksps (perf_xlating shape)"
+    elif name == "cfg3":
+        fs, fmt, rates = 10000000, "cs16", [250000] * 64
+        desc = "cfg3: 64 clients, 10 Msps cs16 -> 250 ksps"
+    elif name == "c512":
+        fs, fmt, rates = 2016000, "cu8", [48000] * 512
+        desc = "cfg4 per-GPU shape: 512 clients, 2.016 Msps cu8 -> 48 ksps"
+    elif name == "c1000":
+        fs, fmt, rates = 2016000, "cu8", [48000] * 1000
+        desc = "target row: 1000 clients, 2.016 Msps cu8 -> 48 ksps"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    tw_for = {}
+    for r in set(rates):
+        if taps_mode == "297" and fs == 2016000:
+            tw_for[r] = 16400      # -> 297 taps (BASELINE.json's figure)
+        elif taps_mode == "297" and fs == 10000000:
+            tw_for[r] = 20060      # -> 1201 taps
+        elif name == "cfg1" and taps_mode == "2429":
+            tw_for[r] = 2000       # test/perf_xlating.c:21
+        else:
+            tw_for[r] = r // 5     # src/dsp_worker.c:98, lpf_cutoff_rate=5
+    C_ = len(rates)
+    plan = []
+    for c, r in enumerate(rates):
+        center = int(round(-fs / 2 + r / 2 + c * (fs - r) / (C_ - 1))) if C_ > 1 else -312000
+        plan.append({"rate": r, "decimation": fs // r, "center": center, "cutoff": r // 2, "tw": tw_for[r]})
+    elem = 2 if fmt == "cs16" else 1
+    return {"name": name, "desc": desc, "fs": fs, "fmt": fmt, "plan": plan,
+            "block_elems": BLOCK_BYTES // elem, "block_samples": BLOCK_BYTES // elem // 2}
+
+
+def synth_blocks(fmt, n_blocks, block_elems, seed):
+    rng = np.random.default_rng(seed)
+    if fmt == "cu8":
+        return rng.integers(0, 256, (n_blocks, block_elems), dtype=np.uint8)
+    if fmt == "cs8":
+        return rng.integers(-128, 128, (n_blocks, block_elems), dtype=np.int8)
+    return rng.integers(-8192, 8192, (n_blocks, block_elems), dtype=np.int16)
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load": the upper half of the samples (idle samples before/after the loop are low)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference's own implementation, thread-per-client (src/dsp_worker.c:41-88)
+# ---------------------------------------------------------------------------
+def cpu_arm(wl, budget_s, flavor=None):
+    from oracle import pyoracle as po  # cpu baseline leg: allowed to use oracle/
+    kind = "reference"
+    if flavor is None:
+        flavor = "avx" if po.ref_available("avx") else ("release" if po.ref_available("release") else None)
+    if flavor is None:
+        kind = "port"
+    ncores = os.cpu_count() or 1
+    plan = wl["plan"]
+    nthreads = min(len(plan), ncores)
+    blocks = synth_blocks(wl["fmt"], 8, wl["block_elems"], seed=4242)
+    tapsets = {}
+    filters = []
+    for p in plan:
+        key = (p["cutoff"], p["tw"])
+        if key not in tapsets:
+            tapsets[key] = (po.ref_lpf_design(1.0, wl["fs"], p["cutoff"], p["tw"], flavor) if kind == "reference"
+                            else po.lpf_design(1.0, wl["fs"], p["cutoff"], p["tw"]))
+        if kind == "reference":
+            filters.append(po.RefFilter(p["decimation"], tapsets[key], p["center"], wl["fs"], wl["block_elems"], flavor))
+        else:
+            filters.append(po.OracleFilter(p["decimation"], tapsets[key], p["center"], wl["fs"], wl["block_elems"]))
+    variant = "optimized"
+    ptrs = [blocks[i].ctypes.data for i in range(len(blocks))]
+    nelem = wl["block_elems"]
+
+    def run_blocks(nblk):
+        def work(tid):
+            mine = filters[tid::nthreads]
+            for b in range(nblk):
+                for f in mine:
+                    if kind == "reference":
+                        f.process_raw(wl["fmt"], ptrs[b % len(ptrs)], nelem, variant)
+                    else:
+                        f.process_cf32(wl["fmt"], blocks[b % len(ptrs)])
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    run_blocks(1)                      # warm-up (page in, first-touch)
+    t1 = max(run_blocks(2) / 2, 1e-6)  # calibrate
+    nblk = int(max(4, min(4000, budget_s / t1)))
+    wall = run_blocks(nblk)
+    msps = nblk * wl["block_samples"] / wall / 1e6
+    status = po.ref_simd_status(flavor) if kind == "reference" else "restatement"
+    return {"value": msps, "unit": "MS/s", "cores": nthreads, "kind": kind,
+            "sample": f"{nblk} blocks of {BLOCK_BYTES} B through all {len(plan)} clients, "
+                      f"{nthreads} threads (thread-per-client, src/dsp_worker.c model), "
+                      f"oracle/_ref/libref_{flavor}.so process_{variant}_* (SIMD_STATUS={status}), wall {wall:.2f} s",
+            "client_msps": msps * len(plan)}
+
+
+# ---------------------------------------------------------------------------
+# main
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--taps", default="default")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(args.workload, args.taps)
+    config = {"workload": wl["desc"], "clients": len(wl["plan"]), "fs": wl["fs"], "input": wl["fmt"],
+              "block_bytes": BLOCK_BYTES, "taps": sorted({(p["rate"], p["tw"]) for p in wl["plan"]}),
+              "streams": "one independent stream per GPU", "l2": "inputs larger than L2 (512 distinct blocks = 134 MB)"}
+
+    # ------------------------------------------------------------------ CPU arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_arm(wl, budget_s=max(10.0, min(60.0, args.steps * 0.05)))
+        line = {"metric": "IQ MS/s in", "value": r["value"], "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": wl["block_samples"] / r["value"] / 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "reference", "config": config, "cpu_baseline": r,
+                "e2e": {"value": r["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("sdr-server_b200")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def build_group(flags):
+        g = pkg.Group(wl["fs"], wl["block_elems"], device=local_rank, flags=flags)
+        tapsets, ids = {}, []
+        for p in wl["plan"]:
+            key = (p["cutoff"], p["tw"])
+            if key not in tapsets:
+                tapsets[key] = pkg.create_low_pass_filter(1.0, wl["fs"], p["cutoff"], p["tw"])
+            ids.append(g.add_client(p["decimation"], tapsets[key], p["center"]))
+        return g, ids, {k: len(v) for k, v in tapsets.items()}
+
+    fmt_code = pkg.FMT[wl["fmt"]]
+    n_dev_blocks = 512
+    host_blocks = synth_blocks(wl["fmt"], n_dev_blocks, wl["block_elems"], seed=1000 + rank)
+    dev = torch.from_numpy(host_blocks.view(np.uint8).reshape(n_dev_blocks, -1)).cuda()
+    blk_stride = dev.stride(0)
+    base_ptr = dev.data_ptr()
+
+    # ---- tier (i): inputs resident in HBM, outputs stay in HBM -> `value`
+    g, ids, taplens = build_group(pkg.XLG_OUT_DEVICE)
+    config["taps_len"] = sorted(set(taplens.values()))
+    step_no = [0]
+
+    def run_steps(k):
+        last = -1
+        for _ in range(k):
+            b = step_no[0] % n_dev_blocks
+            step_no[0] += 1
+            last = g.submit_ptr(fmt_code, base_ptr + b * blk_stride, wl["block_elems"], pkg.XLG_INPUT_DEVICE)
+        return last
+
+    g.wait(run_steps(args.warmup))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    g.timer_start()
+    last = run_steps(args.steps)
+    ms = g.timer_stop()
+    barrier()
+    g.wait(last)
+    # per-kernel pass (CUDA events around every launch, on the launching stream)
+    g.profile_enable(True)
+    g.profile_read(reset=True)
+    last = run_steps(args.steps)
+    g.wait(last)
+    g.profile_enable(False)
+    prof = g.profile_read(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    n_out_total = sum(g.output_ptr(last, c)[1] for c in ids)
+    kinds = sorted({g.client_info(c)[1] for c in ids})
+    g.close()
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * wl["block_samples"] * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- tier (iii): through the C ABI with host buffers -> `e2e`
+    e2e = None
+    if not args.no_e2e:
+        g2, ids2, _ = build_group(0)
+        n_pin = 8
+        pins = [pkg.PinnedBuffer(BLOCK_BYTES) for _ in range(n_pin)]
+        for i, p in enumerate(pins):
+            p.array(np.uint8)[:] = host_blocks[i].view(np.uint8)
+        sink = [0.0]
+
+        def run_e2e(k):
+            pend = []
+            for s in range(k):
+                pend.append(g2.submit_ptr(fmt_code, pins[s % n_pin].ptr, wl["block_elems"], 0))
+                if len(pend) >= pkg.XLG_SLOTS - 1:
+                    tk = pend.pop(0)
+                    g2.wait(tk)
+                    ptr, n = g2.output_ptr(tk, ids2[0])  # the result is in pinned host memory; touch it
+                    sink[0] += n
+            for tk in pend:
+                g2.wait(tk)
+
+        run_e2e(args.warmup)
+        e2e_steps = min(args.steps, 200)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        tw_ = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tw_, op=dist.ReduceOp.MAX)
+        wall = float(tw_.item())
+        e2e = {"value": world * wl["block_samples"] * e2e_steps / wall / 1e6, "unit": "MS/s",
+               "h2d_bytes_per_step": BLOCK_BYTES, "d2h_bytes_per_step": int(n_out_total * 8),
+               "steps": e2e_steps, "timing": "host wall clock around submit..wait of every block (pinned host buffers)"}
+        g2.close()
+        for p in pins:
+            p.free()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    algo_bytes = BLOCK_BYTES + 8 * n_out_total  # read the block once, write cf32 per client
+    roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": peak_src, "kernel": "fir_tile_cf32_kernel", "algorithmic_bytes_per_launch": algo_bytes}
+    fp32 = None
+    if prof["fir_tile_launches"] > 0:
+        k_ms = prof["fir_tile_ms"] / prof["fir_tile_launches"]
+        roof["kernel_ms"] = k_ms
+        roof["achieved"] = algo_bytes / (k_ms * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / hbm_peak
+        algo_fma = 4.0 * prof["algo_macs"] / prof["blocks"]
+        issued_fma = 4.0 * prof["tile_macs"] / prof["blocks"]
+        fp32_peak, fp32_src = 36.3, "fallback: 36.3 TFMA/s measured with bin/microbench on this pool (round 1)"
+        try:
+            out = subprocess.run([os.path.join(ROOT, "sdr-server_b200", "bin", "microbench"), "4000"],
+                                 capture_output=True, text=True, timeout=60).stdout
+            best = max(json.loads(l)["tfma_per_s"] for l in out.splitlines() if '"ffma"' in l)
+            fp32_peak, fp32_src = best, "bin/microbench ffma, measured in this run"
+        except Exception:
+            pass
+        fp32 = {"bound": "fp32_fma", "achieved": algo_fma / (k_ms * 1e-3) / 1e12, "issued": issued_fma / (k_ms * 1e-3) / 1e12,
+                "peak": fp32_peak, "unit": "TFMA/s", "frac": algo_fma / (k_ms * 1e-3) / 1e12 / fp32_peak,
+                "peak_source": fp32_src,
+                "note": "this path is bound by the FP32 FMA pipe, not HBM (DESIGN.md section 4)"}
+        roof["fp32"] = fp32
+    roof["step_kernels_ms"] = {"convert": prof["convert_ms"] / max(prof["convert_launches"], 1),
+                               "phase": prof["phase_ms"] / max(prof["phase_launches"], 1),
+                               "fir_tile": prof["fir_tile_ms"] / max(prof["fir_tile_launches"], 1),
+                               "fir_generic": prof["fir_generic_ms"] / max(prof["fir_generic_launches"], 1)}
+
+    launches_per_step = sum(1 for k in ("convert", "phase", "fir_tile", "fir_generic")
+                            if prof[f"{k}_launches"] > 0)
+    line = {"metric": "IQ MS/s in", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "client_msps": value * len(wl["plan"]),
+            "realtime_clients_per_gpu": int(value / world * len(wl["plan"]) * 1e6 / wl["fs"]),
+            "kernels_used": kinds, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof}
+    if not args.no_cpu and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_arm(wl, budget_s=args.cpu_seconds)
+        except Exception as ex:  # the GPU number stands on its own
+            line["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

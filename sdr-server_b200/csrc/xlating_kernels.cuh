@@ -137,29 +137,68 @@ __global__ void convert_q15_kernel(const void *__restrict__ raw, short2 *__restr
 // from exact math.  One thread per client replays it bit for bit and stores the
 // phase of every output of this block.
 // ---------------------------------------------------------------------------
-__global__ void phase_cf32_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
-                                  float2 *__restrict__ phases, long long S, int n_in) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_clients) return;
+constexpr int P_THREADS = 32;   // one warp per CTA: 32 clients, spread over many SMs
+constexpr int P_CHUNK = 32;     // outputs buffered per client before a coalesced flush
+
+// Each lane owns one client and walks its recursion sequentially; every P_CHUNK
+// steps the warp flushes the 32x32 tile it produced so that each global store is
+// 32 consecutive outputs of ONE client (256 B, coalesced) instead of 32 scattered
+// 8-byte stores (which cost one LSU wavefront each and made this kernel 8x slower
+// than its dependency chain).
+__global__ void __launch_bounds__(P_THREADS)
+phase_cf32_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
+                  float2 *__restrict__ phases, long long S, int n_in) {
+  __shared__ float2 tile[32][P_CHUNK + 1];
+  __shared__ int s_off[32], s_n[32];
+  const int lane = threadIdx.x;
+  const int c = blockIdx.x * 32 + lane;
   ClientDev *d = cl + c;
-  if (!d->active) return;
-  const long long first = S - d->hist;
-  const long long last_ok = S + n_in - d->T;  // last admissible window start (src/xlating.c:58-60)
-  int n_out = 0;
-  if (last_ok >= first) n_out = (int)((last_ok - first) / d->D) + 1;
-  if (n_out > d->out_cap) n_out = d->out_cap;  // cannot happen for input_len <= max_input_len
-  BlkInfo b;
-  b.first = first;
-  b.n_out = n_out;
-  b.pad_ = 0;
-  blk[c] = b;
-  float2 p = d->phase;
-  const float2 inc = d->incr;
-  float2 *row = phases + d->out_off;
-  for (int k = 0; k < n_out; k++) {
-    row[k] = p;
-    p = cmul_unfused(p, inc);  // src/xlating.c:71
+  const bool live = c < n_clients && d->active;
+  int n_out = 0, D = 1;
+  long long first = 0;
+  float2 p = make_float2(1.f, 0.f), inc = make_float2(1.f, 0.f);
+  if (live) {
+    D = d->D;
+    first = S - d->hist;
+    const long long last_ok = S + n_in - d->T;  // last admissible window start (src/xlating.c:58-60)
+    if (last_ok >= first) n_out = (int)((last_ok - first) / D) + 1;
+    if (n_out > d->out_cap) n_out = d->out_cap;  // cannot happen for input_len <= max_input_len
+    BlkInfo b;
+    b.first = first;
+    b.n_out = n_out;
+    b.pad_ = 0;
+    blk[c] = b;
+    p = d->phase;
+    inc = d->incr;
   }
+  s_off[lane] = live ? d->out_off : 0;
+  s_n[lane] = n_out;
+  int n_max = n_out;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, s));
+  __syncwarp();
+  for (int k0 = 0; k0 < n_max; k0 += P_CHUNK) {
+    if (k0 < n_out) {
+#pragma unroll 8
+      for (int j = 0; j < P_CHUNK; j++) {
+        tile[lane][j] = p;           // phase of output k0 + j
+        p = cmul_unfused(p, inc);    // src/xlating.c:71
+      }
+      // the recursion ran past n_out inside the last chunk: rewind is not possible,
+      // so the final phase is re-derived below from the stored tile
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; r++) {
+      const int k = k0 + lane;
+      if (k < s_n[r]) phases[s_off[r] + k] = tile[r][lane];
+    }
+    __syncwarp();
+    if (k0 < n_out && k0 + P_CHUNK > n_out) {
+      // exact phase after the last output: phase of output n_out-1 advanced once
+      p = cmul_unfused(tile[lane][n_out - 1 - k0], inc);
+    }
+  }
+  if (!live) return;
   if (n_out > 0 && d->renorm) {
     // src/xlating.c:73.  glibc's hypotf is (float)sqrt((double)x*x + (double)y*y)
     // (verified on 5e7 random inputs); the products are exact in double.
@@ -169,11 +208,12 @@ __global__ void phase_cf32_kernel(ClientDev *__restrict__ cl, int n_clients, Blk
     p.y = __fdiv_rn(p.y, mag);
   }
   d->phase = p;
-  d->hist = (S + n_in) - (first + (long long)n_out * d->D);  // src/xlating.c:76
+  d->hist = (S + n_in) - (first + (long long)n_out * D);  // src/xlating.c:76
 }
 
-__global__ void phase_q15_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
-                                 short2 *__restrict__ qphases, long long S, int n_in) {
+__global__ void __launch_bounds__(P_THREADS)
+phase_q15_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
+                 short2 *__restrict__ qphases, long long S, int n_in) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_clients) return;
   ClientDev *d = cl + c;
@@ -400,11 +440,10 @@ __device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(T_THREADS)
+__global__ void __launch_bounds__(T_THREADS, 3)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
-                     const float2 *__restrict__ tile_taps, const int *__restrict__ members,
-                     const ClientDev *__restrict__ cl, const float2 *__restrict__ phases,
-                     float2 *__restrict__ out) {
+                     const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
+                     const float2 *__restrict__ phases, float2 *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
   float2 *ts = reinterpret_cast<float2 *>(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + T_STAGES * T_CHUNK_BYTES);
@@ -421,6 +460,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   const int tile = local - grp * K.tiles;
   const int k0 = tile * T_KT;
   const int D = K.D, Dp = K.Dp, L = K.L;
+  const int n_out = K.n_out;
   const int nchunks = (L + T_JC - 1) / T_JC;
 
   if (tid == 0) {
@@ -460,12 +500,20 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  __syncthreads();
 
-  const int *mem = members + K.members_off + grp * T_CG + warp * T_RC;
-  const bool warp_active = mem[0] >= 0;  // members are packed from the front of a group
+  // per-thread output rows of the 8 clients of this warp (-1 = padding slot); loaded
+  // now so the epilogue does not start with a chain of dependent global loads
+  int off[T_RC];
+  {
+    const int *mo = member_off + K.members_off + grp * T_CG + warp * T_RC;
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) off[c] = __ldg(mo + c);
+  }
+  const bool warp_active = off[0] >= 0;  // members are packed from the front of a group
+
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
 
   float2 acc[T_RK][T_RC];
 #pragma unroll
@@ -485,17 +533,33 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       const int len = min(T_JC, L - ch * T_JC);
       const float4 *tp = reinterpret_cast<const float4 *>(ts + s * T_CHUNK_F2 + warp * T_RC);
       const int fbase = ch * T_JC;
+      // operands are fetched one tap ahead of the FMAs that consume them (the
+      // fetch past the end of a chunk reads valid shared memory and is discarded)
+      float2 xn[T_RK];
+      float4 tn[T_RC / 2];
+      xn[0] = xb0[fbase];
+      xn[1] = xb1[fbase];
+      xn[2] = xb2[fbase];
+      xn[3] = xb3[fbase];
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++) tn[q] = tp[q];
+#pragma unroll 1
       for (int f = 0; f < len; f += 8) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           float2 x[T_RK];
-          x[0] = xb0[fbase + f + u];
-          x[1] = xb1[fbase + f + u];
-          x[2] = xb2[fbase + f + u];
-          x[3] = xb3[fbase + f + u];
           float4 tq[T_RC / 2];
 #pragma unroll
-          for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+          for (int i = 0; i < T_RK; i++) x[i] = xn[i];
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) tq[q] = tn[q];
+          const int fn = f + u + 1;
+          xn[0] = xb0[fbase + fn];
+          xn[1] = xb1[fbase + fn];
+          xn[2] = xb2[fbase + fn];
+          xn[3] = xb3[fbase + fn];
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) tn[q] = tp[fn * (T_CG / 2) + q];
 #pragma unroll
           for (int i = 0; i < T_RK; i++) {
 #pragma unroll
@@ -523,20 +587,22 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     }
   }
 
-  // epilogue: derotate with the pre-computed oscillator and store (coalesced in k)
+  // epilogue: derotate with the pre-computed oscillator and store (coalesced in k).
+  // All loads of one client are issued before their first use.
   if (warp_active) {
 #pragma unroll
     for (int c = 0; c < T_RC; c++) {
-      const int m = mem[c];
-      if (m < 0) continue;
-      const int off = cl[m].out_off;
+      if (off[c] < 0) continue;
+      float2 ph[T_RK];
 #pragma unroll
       for (int i = 0; i < T_RK; i++) {
         const int k = k0 + lane + 32 * i;
-        if (k < K.n_out) {
-          const float2 ph = phases[off + k];
-          out[off + k] = cmul_unfused(acc[i][c], ph);  // src/xlating.c:70
-        }
+        ph[i] = (k < n_out) ? __ldg(phases + off[c] + k) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < T_RK; i++) {
+        const int k = k0 + lane + 32 * i;
+        if (k < n_out) out[off[c] + k] = cmul_unfused(acc[i][c], ph[i]);  // src/xlating.c:70
       }
     }
   }
