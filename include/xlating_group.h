@@ -45,6 +45,9 @@ enum { XLG_FMT_CU8 = 0, XLG_FMT_CS8 = 1, XLG_FMT_CS16 = 2 };
 #define XLG_OUT_DEVICE 0x1u    /* leave outputs in HBM (no D2H); xlg_output returns device pointers */
 #define XLG_NO_RENORM 0x2u     /* skip the per-call phase renormalisation (AVX variant, src/xlating.c:336-339) */
 #define XLG_FORCE_GENERIC 0x4u /* route every client through the generic kernel (testing) */
+#define XLG_SM_PARTITION 0x10u /* reserve 8 SMs (CUDA green context) for the oscillator pre-pass so that it
+                                  overlaps the FIR of the previous block without fighting it for issue slots;
+                                  meant for throughput-bound deployments with many high-rate clients */
 /* xlg_submit flags */
 #define XLG_INPUT_DEVICE 0x100u /* `input` is a device pointer on the group's GPU (already staged) */
 #define XLG_PATH_Q15 0x200u     /* Q15 integer path (src/xlating.c:92-140) instead of cf32 */

@@ -35,6 +35,7 @@ NP_DTYPE = {"cu8": np.uint8, "cs8": np.int8, "cs16": np.int16}
 XLG_OUT_DEVICE = 0x1
 XLG_NO_RENORM = 0x2
 XLG_FORCE_GENERIC = 0x4
+XLG_SM_PARTITION = 0x10
 XLG_INPUT_DEVICE = 0x100
 XLG_PATH_Q15 = 0x200
 XLG_SLOTS = 4

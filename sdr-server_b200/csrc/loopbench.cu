@@ -1,0 +1,233 @@
+/*
+ * csrc/loopbench.cu -- inner-loop ceiling of the tiled FIR kernels.
+ *
+ * Runs only the shared-memory-load + FMA body of fir_tile_cf32_kernel (scalar FFMA,
+ * 4 outputs x 8 clients per thread) and fir_tile2_cf32_kernel (packed FFMA2,
+ * 4 x 4 per thread, half-warp broadcast) over data that is already resident in
+ * shared memory: no TMA, no barriers, no staging, no epilogue.  The gap between
+ * this number and bin/microbench (registers only) is what the shared-memory
+ * operand traffic costs; the gap between the real kernels and this number is
+ * what everything else costs.  Usage: loopbench [iters]
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+constexpr int DP = 43;
+constexpr int LFLAT = 96;    // flat taps per pass (small enough for 3 CTAs/SM)
+
+// ---- variant 1: scalar FFMA, lane = output, 4 outputs x 8 clients ----
+template <int PREFETCH>
+__global__ void __launch_bounds__(128, 3) k_v1(float *out, int passes, long long *cycles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2 *ts = reinterpret_cast<float2 *>(smem);                  // [LFLAT][32]
+  float2 *xs = reinterpret_cast<float2 *>(smem + LFLAT * 32 * 8); // 127*DP + LFLAT
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int xs_len = 127 * DP + LFLAT + 8;
+  for (int i = tid; i < LFLAT * 32; i += 128) ts[i] = make_float2(0.001f * (i % 13), 0.002f * (i % 7));
+  for (int i = tid; i < xs_len; i += 128) xs[i] = make_float2(0.01f * (i % 11), 0.02f * (i % 5));
+  __syncthreads();
+  float2 acc[4][8];
+  for (int i = 0; i < 4; i++)
+    for (int c = 0; c < 8; c++) acc[i][c] = make_float2(0.f, 0.f);
+  const float2 *xb0 = xs + lane * DP, *xb1 = xb0 + 32 * DP, *xb2 = xb1 + 32 * DP, *xb3 = xb2 + 32 * DP;
+  const float4 *tp = reinterpret_cast<const float4 *>(ts + warp * 8);
+  long long t0 = clock64();
+  for (int p = 0; p < passes; p++) {
+#pragma unroll 1
+    for (int f = 0; f < LFLAT; f += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        float2 x[4];
+        x[0] = xb0[f + u];
+        x[1] = xb1[f + u];
+        x[2] = xb2[f + u];
+        x[3] = xb3[f + u];
+        float4 tq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) tq[q] = tp[(f + u) * 16 + q];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+            a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+            a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+            a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+            a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+            a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+            a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+            a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+            a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+          }
+      }
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+  for (int i = 0; i < 4; i++)
+    for (int c = 0; c < 8; c++) s += acc[i][c].x + acc[i][c].y;
+  out[blockIdx.x * 128 + tid] = s;
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// ---- variant 2: packed FFMA2, lane = (h, o), 4 outputs x 4 clients, two accumulators ----
+template <int MODE>  // 0: plain, 1: ping-pong prefetch
+__global__ void __launch_bounds__(128, 4) k_v2(float *out, int passes, long long *cycles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  ulonglong2 *ts = reinterpret_cast<ulonglong2 *>(smem);          // [LFLAT][32] x 16 B
+  float2 *xs = reinterpret_cast<float2 *>(smem + LFLAT * 32 * 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, o = lane & 15, h = lane >> 4;
+  const int xs_len = 63 * DP + LFLAT + 8;
+  float4 *tf = reinterpret_cast<float4 *>(ts);
+  for (int i = tid; i < LFLAT * 32; i += 128) {
+    float a = 0.001f * (i % 13), b = 0.002f * (i % 7);
+    tf[i] = make_float4(a, a, b, b);
+  }
+  for (int i = tid; i < xs_len; i += 128) xs[i] = make_float2(0.01f * (i % 11), 0.02f * (i % 5));
+  __syncthreads();
+  u64 A1[4][4], A2[4][4];
+  for (int i = 0; i < 4; i++)
+    for (int q = 0; q < 4; q++) A1[i][q] = A2[i][q] = 0ull;
+  const u64 *xq = reinterpret_cast<const u64 *>(xs);
+  const u64 *xb0 = xq + o * DP, *xb1 = xb0 + 16 * DP, *xb2 = xb1 + 16 * DP, *xb3 = xb2 + 16 * DP;
+  const ulonglong2 *tp = ts + warp * 8 + h * 4;
+  long long t0 = clock64();
+  for (int p = 0; p < passes; p++) {
+    if (MODE == 0) {
+#pragma unroll 1
+      for (int f = 0; f < LFLAT; f += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          u64 x[4];
+          x[0] = xb0[f + u];
+          x[1] = xb1[f + u];
+          x[2] = xb2[f + u];
+          x[3] = xb3[f + u];
+          ulonglong2 t[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) t[q] = tp[(f + u) * 32 + q];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              A1[i][q] = ffma2(x[i], t[q].x, A1[i][q]);
+              A2[i][q] = ffma2(x[i], t[q].y, A2[i][q]);
+            }
+        }
+      }
+    } else {
+      u64 xa[4], xb[4];
+      ulonglong2 ta[4], tb[4];
+      xa[0] = xb0[0];
+      xa[1] = xb1[0];
+      xa[2] = xb2[0];
+      xa[3] = xb3[0];
+#pragma unroll
+      for (int q = 0; q < 4; q++) ta[q] = tp[q];
+#pragma unroll 1
+      for (int f = 0; f < LFLAT; f += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          xb[0] = xb0[f + u + 1];
+          xb[1] = xb1[f + u + 1];
+          xb[2] = xb2[f + u + 1];
+          xb[3] = xb3[f + u + 1];
+#pragma unroll
+          for (int q = 0; q < 4; q++) tb[q] = tp[(f + u + 1) * 32 + q];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              A1[i][q] = ffma2(xa[i], ta[q].x, A1[i][q]);
+              A2[i][q] = ffma2(xa[i], ta[q].y, A2[i][q]);
+            }
+          xa[0] = xb0[f + u + 2];
+          xa[1] = xb1[f + u + 2];
+          xa[2] = xb2[f + u + 2];
+          xa[3] = xb3[f + u + 2];
+#pragma unroll
+          for (int q = 0; q < 4; q++) ta[q] = tp[(f + u + 2) * 32 + q];
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              A1[i][q] = ffma2(xb[i], tb[q].x, A1[i][q]);
+              A2[i][q] = ffma2(xb[i], tb[q].y, A2[i][q]);
+            }
+        }
+      }
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+  for (int i = 0; i < 4; i++)
+    for (int q = 0; q < 4; q++) {
+      float2 a = unpack2(A1[i][q]), b = unpack2(A2[i][q]);
+      s += a.x + a.y + b.x + b.y;
+    }
+  out[blockIdx.x * 128 + tid] = s;
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <typename K>
+static void run(const char *name, K kernel, int per_sm, size_t smem, int passes, double fma_per_thread_pass,
+                float *d_out, long long *d_cyc, int sms) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int blocks = per_sm * sms;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  kernel<<<blocks, 128, smem>>>(d_out, 2, d_cyc);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    printf("{\"bench\": \"%s\", \"error\": \"%s\"}\n", name, cudaGetErrorString(err));
+    return;
+  }
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    kernel<<<blocks, 128, smem>>>(d_out, passes, d_cyc);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  const double total = fma_per_thread_pass * passes * 128.0 * blocks;
+  printf("{\"bench\": \"%s\", \"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"tfma_per_s\": %.3f, \"ms\": %.4f}\n", name,
+         per_sm, per_sm * 4, total / (best * 1e-3) / 1e12, best);
+}
+
+int main(int argc, char **argv) {
+  int passes = argc > 1 ? atoi(argv[1]) : 1000;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, 0);
+  const int sms = prop.multiProcessorCount;
+  float *d_out;
+  long long *d_cyc;
+  cudaMalloc(&d_out, sizeof(float) * 148 * 8 * 128);
+  cudaMalloc(&d_cyc, sizeof(long long) * 148 * 8);
+  const size_t smem1 = (size_t)LFLAT * 32 * 8 + (127 * DP + LFLAT + 8) * 8;   // 131 KB + 48 KB
+  const size_t smem2 = (size_t)LFLAT * 32 * 16 + (63 * DP + LFLAT + 8) * 8;
+  printf("{\"smem_v1\": %zu, \"smem_v2\": %zu}\n", smem1, smem2);
+  for (int per_sm = 1; per_sm <= 3; per_sm++) {
+    run("v1_ffma_4x8", k_v1<0>, per_sm, smem1, passes, LFLAT * 128.0, d_out, d_cyc, sms);
+    run("v2_ffma2_4x4_plain", k_v2<0>, per_sm, smem2, passes, LFLAT * 64.0, d_out, d_cyc, sms);
+    run("v2_ffma2_4x4_pingpong", k_v2<1>, per_sm, smem2, passes, LFLAT * 64.0, d_out, d_cyc, sms);
+  }
+  return 0;
+}

@@ -93,6 +93,34 @@ __global__ void k_ffma2(float *out, const float *in, int iters, long long *cycle
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// dependent-chain latency of the oscillator recursion p <- p*inc (unfused complex
+// multiply): MODE 0 = FMUL/FADD as written, MODE 1 = the same roundings expressed
+// with FFMA only (fma(a,b,-0) == round(a*b); fma(x,1,-y) == round(x-y))
+template <int MODE>
+__global__ void k_chain(float *out, const float *in, int steps, long long *cycles) {
+  float pr = in[threadIdx.x] + 1.0f, pi = in[threadIdx.x + 32];
+  const float ir = 0.99f + in[1], ii = 0.1f + in[2];
+  long long t0 = clock64();
+#pragma unroll 8
+  for (int k = 0; k < steps; k++) {
+    float nr, ni;
+    if (MODE == 0) {
+      nr = __fsub_rn(__fmul_rn(pr, ir), __fmul_rn(pi, ii));
+      ni = __fadd_rn(__fmul_rn(pr, ii), __fmul_rn(pi, ir));
+    } else {
+      const float a = __fmaf_rn(pr, ir, -0.0f), b = __fmaf_rn(pi, ii, -0.0f);
+      const float c = __fmaf_rn(pr, ii, -0.0f), d = __fmaf_rn(pi, ir, -0.0f);
+      nr = __fmaf_rn(a, 1.0f, -b);
+      ni = __fmaf_rn(c, 1.0f, d);
+    }
+    pr = nr;
+    pi = ni;
+  }
+  long long t1 = clock64();
+  out[threadIdx.x] = pr + pi;
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 template <typename K>
 static void run(const char *name, K kernel, int blocks_per_sm, int threads, int iters, int sms, float *d_out,
                 float *d_in, long long *d_cyc) {
@@ -151,6 +179,18 @@ int main(int argc, char **argv) {
   for (auto &c : cfg) {
     run("ffma", k_ffma, c[0], c[1], iters, sms, d_out, d_in, d_cyc);
     run("ffma2", k_ffma2, c[0], c[1], iters, sms, d_out, d_in, d_cyc);
+  }
+  for (int mode = 0; mode < 2; mode++) {
+    const int steps = 100000;
+    if (mode == 0)
+      k_chain<0><<<1, 32>>>(d_out, d_in, steps, d_cyc);
+    else
+      k_chain<1><<<1, 32>>>(d_out, d_in, steps, d_cyc);
+    cudaDeviceSynchronize();
+    long long cyc = 0;
+    cudaMemcpy(&cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost);
+    printf("{\"bench\": \"osc_chain_%s\", \"cycles_per_step\": %.2f}\n", mode == 0 ? "fmul_fadd" : "ffma_only",
+           (double)cyc / steps);
   }
   return 0;
 }

@@ -22,6 +22,7 @@
  * The reference's per-client dsp loop this replaces: src/dsp_worker.c:41-88 calling
  * src/xlating.c:384-414 -> :52-83 once per client per block.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdio.h>
@@ -75,6 +76,7 @@ struct HostClient {
   int kind = 0;
   int out_off = 0, out_cap = 0;
   int taps_off = 0;
+  int ph_off = 0;
 };
 
 struct Slot {
@@ -96,6 +98,42 @@ struct Slot {
   uint64_t tile_macs = 0, algo_macs = 0, out_samples = 0, in_samples = 0;
 };
 
+// Optional spatial partition of the GPU (CUDA green contexts): the oscillator
+// pre-pass is a latency-bound dependent chain (8-14 cycles per output, one lane
+// per client); when it shares an SM sub-partition with FIR warps that can issue an
+// FMA every cycle it loses the issue arbitration and runs 3x slower, which then
+// bounds the whole pipeline.  Giving it 8 SMs of its own (the minimum partition on
+// sm_90+) and the FIR the other 140 costs the FIR 5.4 % and removes that stall.
+// The driver entry points are resolved at run time (cudaGetDriverEntryPoint) so
+// the library has no link-time dependency on libcuda.
+struct SmPartition {
+  CUgreenCtx small_ctx = nullptr, big_ctx = nullptr;
+  int small_sms = 0, big_sms = 0;
+  bool ok = false;
+};
+
+typedef CUresult (*pfn_cuDeviceGet)(CUdevice *, int);
+typedef CUresult (*pfn_cuDeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType);
+typedef CUresult (*pfn_cuDevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *,
+                                                    CUdevResource *, unsigned int, unsigned int);
+typedef CUresult (*pfn_cuDevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+typedef CUresult (*pfn_cuGreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*pfn_cuGreenCtxDestroy)(CUgreenCtx);
+typedef CUresult (*pfn_cuGreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int);
+
+template <typename F>
+static bool drv(const char *name, F *fn) {
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess ||
+      p == nullptr) {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = reinterpret_cast<F>(p);
+  return true;
+}
+
 struct TileClassHost {
   TileClass k;
   std::vector<int> members;
@@ -110,6 +148,7 @@ struct xlg_group {
   uint32_t max_input_len = 0;  // scalar elements
   uint32_t flags = 0;
   cudaStream_t s_in = nullptr, s_ph = nullptr, s_c = nullptr, s_c2 = nullptr, s_out = nullptr;
+  SmPartition part;
 
   float2 *ring = nullptr;
   short2 *qring = nullptr;
@@ -122,8 +161,12 @@ struct xlg_group {
   size_t d_clients_cap = 0;
   float2 *d_taps = nullptr;
   short2 *d_qtaps = nullptr;
-  float2 *d_tile_taps = nullptr;
+  void *d_tile_taps = nullptr;
+  int tile_ver = 1;       // 1 = scalar-FFMA tile kernel (faster, default), 2 = packed FFMA2 tile kernel
   int *d_members = nullptr;
+  int *d_order = nullptr;   // clients in oscillator-table order, 32 per group, -1 = padding
+  int n_order = 0;
+  size_t phase_cap = 0;     // float2 per slot oscillator table
   size_t arena_cap = 0;   // complex samples per slot arena
   bool q_alloc = false;
 
@@ -267,11 +310,8 @@ static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
     for (Slot &s : g->slots) {
       if (s.d_out) cudaFree(s.d_out);
       if (s.h_out) cudaFreeHost(s.h_out);
-      if (s.d_phases) cudaFree(s.d_phases);
       s.d_out = s.h_out = nullptr;
-      s.d_phases = nullptr;
       CU_OK(cudaMalloc(&s.d_out, cap * sizeof(float2)));
-      CU_OK(cudaMalloc(&s.d_phases, cap * sizeof(float2)));
       if (!dev_out) CU_OK(cudaHostAlloc(&s.h_out, cap * sizeof(float2), cudaHostAllocDefault));
       if (g->q_alloc) {
         if (s.d_qout) cudaFree(s.d_qout);
@@ -365,7 +405,10 @@ static int rebuild_layout(xlg_group *g) {
     if (!(g->flags & XLG_FORCE_GENERIC) && settled) buckets[std::make_tuple(h.D, h.T, h.hist)].push_back(i);
   }
   std::vector<int> members;
-  std::vector<float2> tile_taps;
+  std::vector<float2> tile_taps;  // v1: one float2 per client-tap; v2: two (tr,tr),(ti,ti)
+  const int KT = g->tile_ver == 2 ? U_KT : T_KT;
+  const int per_tap = g->tile_ver == 2 ? 2 : 1;
+  const size_t smem_fixed = g->tile_ver == 2 ? (size_t)U_SMEM_FIXED : (size_t)T_SMEM_FIXED;
   for (auto &kv : buckets) {
     const uint32_t D = std::get<0>(kv.first);
     const size_t T = std::get<1>(kv.first);
@@ -374,8 +417,8 @@ static int rebuild_layout(xlg_group *g) {
     const int Dp = (int)(D | 1u);
     const size_t q_last = (T - 1) / D, r_last = (T - 1) % D;
     const int L = (int)(((q_last * Dp + r_last + 1) + 7) / 8 * 8);
-    const int xs_len = (T_KT - 1) * Dp + L;
-    const size_t smem = (size_t)T_SMEM_FIXED + ((size_t)xs_len + 8) * sizeof(float2);
+    const int xs_len = (KT - 1) * Dp + L;
+    const size_t smem = smem_fixed + ((size_t)xs_len + 8) * sizeof(float2);
     const size_t typical_out = g->max_input_len / 2 / D;
     if (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs) continue;
     if ((int)g->classes.size() >= T_MAX_CLASSES) continue;
@@ -389,10 +432,10 @@ static int rebuild_layout(xlg_group *g) {
     ch.k.xs_len = xs_len;
     ch.k.n_groups = (int)((ids.size() + T_CG - 1) / T_CG);
     ch.k.members_off = (int)members.size();
-    ch.k.taps_off = (long long)tile_taps.size();
+    ch.k.taps_off = (long long)(tile_taps.size() / per_tap);
     for (int gi = 0; gi < ch.k.n_groups; gi++) {
       const size_t base = tile_taps.size();
-      tile_taps.resize(base + (size_t)L * T_CG, make_float2(0.f, 0.f));
+      tile_taps.resize(base + (size_t)L * T_CG * per_tap, make_float2(0.f, 0.f));
       for (int m = 0; m < T_CG; m++) {
         const size_t idx = (size_t)gi * T_CG + m;
         if (idx >= ids.size()) {
@@ -405,7 +448,12 @@ static int rebuild_layout(xlg_group *g) {
         const HostClient &h = g->clients[id];
         for (size_t j = 0; j < T; j++) {
           const size_t f = (j / D) * Dp + (j % D);
-          tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+          if (per_tap == 1) {
+            tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+          } else {
+            tile_taps[base + (f * T_CG + m) * 2] = make_float2(h.rev[2 * j], h.rev[2 * j]);
+            tile_taps[base + (f * T_CG + m) * 2 + 1] = make_float2(h.rev[2 * j + 1], h.rev[2 * j + 1]);
+          }
         }
       }
     }
@@ -414,7 +462,7 @@ static int rebuild_layout(xlg_group *g) {
   // heaviest classes first: their CTAs are scheduled first and the lighter ones
   // fill the tail of the launch
   std::sort(g->classes.begin(), g->classes.end(), [](const TileClassHost &a, const TileClassHost &b) {
-    return (long long)a.k.L * T_KT > (long long)b.k.L * T_KT;
+    return a.k.L > b.k.L;
   });
   if (g->d_tile_taps) cudaFree(g->d_tile_taps);
   if (g->d_members) cudaFree(g->d_members);
@@ -425,6 +473,62 @@ static int rebuild_layout(xlg_group *g) {
     CU_OK(cudaMemcpy(g->d_tile_taps, tile_taps.data(), tile_taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU_OK(cudaMalloc(&g->d_members, members.size() * sizeof(int)));
     CU_OK(cudaMemcpy(g->d_members, members.data(), members.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+
+  // 3b. oscillator-table order: tile classes (the order the tiled kernel walks them),
+  //     then generic clients; 32 clients per table group
+  {
+    std::vector<int> order;
+    size_t table = 0;
+    for (TileClassHost &ch : g->classes) {
+      int cap = 0;
+      for (int id : ch.members) cap = std::max(cap, g->clients[id].out_cap);
+      ch.k.ph_base = (long long)table;
+      ch.k.ph_stride = cap * 32;
+      for (int gi = 0; gi < ch.k.n_groups; gi++) {
+        for (int m = 0; m < T_CG; m++) {
+          const size_t idx = (size_t)gi * T_CG + m;
+          if (idx < ch.members.size()) {
+            g->clients[ch.members[idx]].ph_off = (int)(table + m);
+            order.push_back(ch.members[idx]);
+          } else {
+            order.push_back(-1);
+          }
+        }
+        table += (size_t)cap * 32;
+      }
+    }
+    std::vector<int> loose;
+    for (int i = 0; i < nc; i++)
+      if (g->clients[i].active && g->clients[i].kind == 0) loose.push_back(i);
+    for (size_t base = 0; base < loose.size(); base += 32) {
+      int cap = 0;
+      for (size_t m = base; m < std::min(base + 32, loose.size()); m++) cap = std::max(cap, g->clients[loose[m]].out_cap);
+      for (size_t m = 0; m < 32; m++) {
+        if (base + m < loose.size()) {
+          g->clients[loose[base + m]].ph_off = (int)(table + m);
+          order.push_back(loose[base + m]);
+        } else {
+          order.push_back(-1);
+        }
+      }
+      table += (size_t)cap * 32;
+    }
+    if (g->d_order) cudaFree(g->d_order);
+    g->d_order = nullptr;
+    g->n_order = (int)order.size();
+    if (!order.empty()) {
+      CU_OK(cudaMalloc(&g->d_order, order.size() * sizeof(int)));
+      CU_OK(cudaMemcpy(g->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (table > g->phase_cap) {
+      g->phase_cap = table + table / 4 + 1024;
+      for (Slot &sl : g->slots) {
+        if (sl.d_phases) cudaFree(sl.d_phases);
+        sl.d_phases = nullptr;
+        CU_OK(cudaMalloc(&sl.d_phases, g->phase_cap * sizeof(float2)));
+      }
+    }
   }
 
   // 4. device client table
@@ -457,6 +561,7 @@ static int rebuild_layout(xlg_group *g) {
     d.active = 1;
     d.kind = h.kind;
     d.renorm = (g->flags & XLG_NO_RENORM) ? 0 : 1;
+    d.ph_off = h.ph_off;
     if (h.kind == 0) g->n_generic++;
   }
   if ((size_t)nc > g->d_clients_cap) {
@@ -478,6 +583,48 @@ static int rebuild_layout(xlg_group *g) {
   }
   g->dirty = false;
   return 0;
+}
+
+// Split the device into an 8-SM partition (oscillator pre-pass) and the rest (FIR)
+// and create the compute streams inside them.  Any failure leaves part.ok false
+// and the group falls back to ordinary streams.
+static void partition_create(xlg_group *g, int device) {
+  pfn_cuDeviceGet p_devget;
+  pfn_cuDeviceGetDevResource p_getres;
+  pfn_cuDevSmResourceSplitByCount p_split;
+  pfn_cuDevResourceGenerateDesc p_desc;
+  pfn_cuGreenCtxCreate p_create;
+  pfn_cuGreenCtxStreamCreate p_stream;
+  if (!drv("cuDeviceGet", &p_devget) || !drv("cuDeviceGetDevResource", &p_getres) ||
+      !drv("cuDevSmResourceSplitByCount", &p_split) || !drv("cuDevResourceGenerateDesc", &p_desc) ||
+      !drv("cuGreenCtxCreate", &p_create) || !drv("cuGreenCtxStreamCreate", &p_stream)) {
+    XL_LOG("green contexts unavailable in this driver; SM partition disabled");
+    return;
+  }
+  cudaFree(0);  // make sure the primary context exists
+  CUdevice dev;
+  CUdevResource all, small, rest;
+  unsigned int groups = 1;
+  CUdevResourceDesc d_small = nullptr, d_rest = nullptr;
+  CUstream st_ph = nullptr, st_c = nullptr, st_c2 = nullptr;
+  if (p_devget(&dev, device) != CUDA_SUCCESS || p_getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
+      p_split(&small, &groups, &all, &rest, 0, 8) != CUDA_SUCCESS || groups != 1 ||
+      p_desc(&d_small, &small, 1) != CUDA_SUCCESS || p_desc(&d_rest, &rest, 1) != CUDA_SUCCESS ||
+      p_create(&g->part.small_ctx, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+      p_create(&g->part.big_ctx, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+      p_stream(&st_ph, g->part.small_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      p_stream(&st_c, g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      p_stream(&st_c2, g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+    XL_LOG("could not create the SM partition (green contexts); continuing without it");
+    cudaGetLastError();
+    return;
+  }
+  g->part.small_sms = (int)small.sm.smCount;
+  g->part.big_sms = (int)rest.sm.smCount;
+  g->s_ph = (cudaStream_t)st_ph;
+  g->s_c = (cudaStream_t)st_c;
+  g->s_c2 = (cudaStream_t)st_c2;
+  g->part.ok = true;
 }
 
 // ---------------------------------------------------------------------------
@@ -516,12 +663,21 @@ extern "C" int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input
     xlg_destroy(g);
     return code;
   };
+  {
+    bool want = (flags & XLG_SM_PARTITION) != 0;
+    const char *pe = getenv("XLATING_B200_PARTITION");
+    if (pe != nullptr) want = atoi(pe) != 0;
+    if (want) partition_create(g, device);
+  }
   if (cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&g->s_c, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&g->s_c2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking) != cudaSuccess)
     return fail(-EIO);
+  if (!g->part.ok) {
+    if (cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&g->s_c, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&g->s_c2, cudaStreamNonBlocking) != cudaSuccess)
+      return fail(-EIO);
+  }
   const size_t raw_bytes = (size_t)max_input_len * 2;  // cs16 worst case
   for (Slot &s : g->slots) {
     if (cudaMalloc(&s.d_raw, raw_bytes) != cudaSuccess) return fail(-ENOMEM);
@@ -535,8 +691,14 @@ extern "C" int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input
   if (cudaEventCreateWithFlags(&g->ev_last_conv, cudaEventDisableTiming) != cudaSuccess) return fail(-EIO);
   if (cudaEventCreate(&g->ev_t0) != cudaSuccess || cudaEventCreate(&g->ev_t1) != cudaSuccess) return fail(-EIO);
   // the tiled kernel needs > 48 KiB of dynamic shared memory
+  {
+    const char *tv = getenv("XLATING_B200_TILE");
+    if (tv != nullptr && atoi(tv) == 2) g->tile_ver = 2;
+  }
   if (cudaFuncSetAttribute(fir_tile_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
-      cudaSuccess) {
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
@@ -572,11 +734,19 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_qtaps) cudaFree(g->d_qtaps);
   if (g->d_tile_taps) cudaFree(g->d_tile_taps);
   if (g->d_members) cudaFree(g->d_members);
+  if (g->d_order) cudaFree(g->d_order);
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_ph) cudaStreamDestroy(g->s_ph);
   if (g->s_c) cudaStreamDestroy(g->s_c);
   if (g->s_c2) cudaStreamDestroy(g->s_c2);
   if (g->s_out) cudaStreamDestroy(g->s_out);
+  if (g->part.small_ctx || g->part.big_ctx) {
+    pfn_cuGreenCtxDestroy p_destroy;
+    if (drv("cuGreenCtxDestroy", &p_destroy)) {
+      if (g->part.small_ctx) p_destroy(g->part.small_ctx);
+      if (g->part.big_ctx) p_destroy(g->part.big_ctx);
+    }
+  }
   delete g;
 }
 
@@ -780,11 +950,12 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       CU_OK(cudaEventRecord(s.pf[2], g->s_ph));
       s.pf_phase = true;
     }
-    const int blocks = (nc + P_THREADS - 1) / P_THREADS;
     if (q15)
-      phase_q15_kernel<<<blocks, P_THREADS, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk, s.d_qphases, S, n);
+      phase_q15_kernel<<<(nc + P_QTHREADS - 1) / P_QTHREADS, P_QTHREADS, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk,
+                                                                                      s.d_qphases, S, n);
     else
-      phase_cf32_kernel<<<blocks, P_THREADS, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk, s.d_phases, S, n);
+      phase_cf32_kernel<<<g->n_order / 32, P_THREADS, 0, g->s_ph>>>(g->d_clients, g->d_order, s.d_blk, s.d_phases, S,
+                                                                   n);
     if (g->profiling) CU_OK(cudaEventRecord(s.pf[3], g->s_ph));
     CU_OK(cudaEventRecord(s.ev_phase, g->s_ph));
     CU_OK(cudaStreamWaitEvent(cs, s.ev_phase, 0));
@@ -804,20 +975,26 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       // hist was already advanced above; recover this block's window start
       k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
       k.n_out = n_out;
-      k.tiles = (n_out + T_KT - 1) / T_KT;
+      const int KT = g->tile_ver == 2 ? U_KT : T_KT;
+      k.tiles = (n_out + KT - 1) / KT;
       k.cta_begin = ctas;
       ctas += k.tiles * k.n_groups;
-      smem = std::max(smem, (size_t)T_SMEM_FIXED + ((size_t)k.xs_len + 8) * sizeof(float2));
+      smem = std::max(smem, (size_t)(g->tile_ver == 2 ? U_SMEM_FIXED : T_SMEM_FIXED) +
+                                ((size_t)k.xs_len + 8) * sizeof(float2));
       P.cls[P.n_classes++] = k;
-      s.tile_macs += (uint64_t)k.tiles * T_KT * (uint64_t)k.L * (uint64_t)ch.members.size();
+      s.tile_macs += (uint64_t)k.tiles * KT * (uint64_t)k.L * (uint64_t)ch.members.size();
     }
     if (ctas > 0) {
       if (g->profiling) {
         CU_OK(cudaEventRecord(s.pf[4], cs));
         s.pf_tile = true;
       }
-      fir_tile_cf32_kernel<<<ctas, T_THREADS, smem, cs>>>(P, g->ring, mask, g->d_tile_taps, g->d_members,
-                                                             s.d_phases, s.d_out);
+      if (g->tile_ver == 2)
+        fir_tile2_cf32_kernel<<<ctas, U_THREADS, smem, cs>>>(P, g->ring, mask, (const float4 *)g->d_tile_taps,
+                                                            g->d_members, s.d_phases, s.d_out);
+      else
+        fir_tile_cf32_kernel<<<ctas, T_THREADS, smem, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
+                                                           g->d_members, s.d_phases, s.d_out);
       if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], cs));
     }
   }

@@ -54,7 +54,7 @@ struct ClientDev {
   int active;
   int kind;               // 0 = generic kernel, 1 = tiled kernel
   int renorm;             // 1 = native behaviour (:73), 0 = AVX behaviour (:336-339)
-  int pad_;
+  int ph_off;             // cf32 oscillator table: phase of output k lives at phases[ph_off + 32*k]
 };
 
 struct BlkInfo {
@@ -137,68 +137,47 @@ __global__ void convert_q15_kernel(const void *__restrict__ raw, short2 *__restr
 // from exact math.  One thread per client replays it bit for bit and stores the
 // phase of every output of this block.
 // ---------------------------------------------------------------------------
-constexpr int P_THREADS = 32;   // one warp per CTA: 32 clients, spread over many SMs
-constexpr int P_CHUNK = 32;     // outputs buffered per client before a coalesced flush
+constexpr int P_THREADS = 32;   // one warp = one table group of 32 clients
+constexpr int P_QTHREADS = 64;  // Q15 variant (one thread per client)
 
-// Each lane owns one client and walks its recursion sequentially; every P_CHUNK
-// steps the warp flushes the 32x32 tile it produced so that each global store is
-// 32 consecutive outputs of ONE client (256 B, coalesced) instead of 32 scattered
-// 8-byte stores (which cost one LSU wavefront each and made this kernel 8x slower
-// than its dependency chain).
+// Oscillator table layout: clients are taken in "table order" (tile classes first,
+// in the order the tiled kernel walks them, then the generic clients), 32 per
+// group; group g stores phase(k, lane) at phases[base_g + 32*k + lane].  Lane l of
+// the warp owns client order[32*g + l] and walks its recursion sequentially -- the
+// dependent chain (2 fp32 ops, 10.75 cycles per output measured on B200) is the
+// only thing on the critical path: the per-output store is one coalesced 256-byte
+// line for the whole warp, there is no shared memory, no barrier.  (Earlier
+// versions stored [client][k] rows -- first uncoalesced, then through a shared-
+// memory transpose with helper warps -- and spent 2/3 of their time on that.)
 __global__ void __launch_bounds__(P_THREADS)
-phase_cf32_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
+phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, BlkInfo *__restrict__ blk,
                   float2 *__restrict__ phases, long long S, int n_in) {
-  __shared__ float2 tile[32][P_CHUNK + 1];
-  __shared__ int s_off[32], s_n[32];
-  const int lane = threadIdx.x;
-  const int c = blockIdx.x * 32 + lane;
+  const int c = order[blockIdx.x * 32 + threadIdx.x];
+  if (c < 0) return;
   ClientDev *d = cl + c;
-  const bool live = c < n_clients && d->active;
-  int n_out = 0, D = 1;
-  long long first = 0;
-  float2 p = make_float2(1.f, 0.f), inc = make_float2(1.f, 0.f);
-  if (live) {
-    D = d->D;
-    first = S - d->hist;
-    const long long last_ok = S + n_in - d->T;  // last admissible window start (src/xlating.c:58-60)
-    if (last_ok >= first) n_out = (int)((last_ok - first) / D) + 1;
-    if (n_out > d->out_cap) n_out = d->out_cap;  // cannot happen for input_len <= max_input_len
-    BlkInfo b;
-    b.first = first;
-    b.n_out = n_out;
-    b.pad_ = 0;
-    blk[c] = b;
-    p = d->phase;
-    inc = d->incr;
+  if (!d->active) return;
+  const int D = d->D;
+  const long long first = S - d->hist;
+  const long long last_ok = S + n_in - d->T;  // last admissible window start (src/xlating.c:58-60)
+  int n_out = 0;
+  if (last_ok >= first) n_out = (int)((last_ok - first) / D) + 1;
+  if (n_out > d->out_cap) n_out = d->out_cap;  // cannot happen for input_len <= max_input_len
+  BlkInfo b;
+  b.first = first;
+  b.n_out = n_out;
+  b.pad_ = 0;
+  blk[c] = b;
+  float2 p = d->phase;
+  const float2 inc = d->incr;
+  float2 *dst = phases + d->ph_off;
+  // unrolled 32x: a global store keeps its source registers reserved until the LSU
+  // has read them (a long-scoreboard release, ~100+ cycles); with a short unroll the
+  // recursion stalls on that write-after-read hazard when the registers come round
+#pragma unroll 32
+  for (int k = 0; k < n_out; k++) {
+    dst[(size_t)k * 32] = p;   // phase of output k
+    p = cmul_unfused(p, inc);  // src/xlating.c:71
   }
-  s_off[lane] = live ? d->out_off : 0;
-  s_n[lane] = n_out;
-  int n_max = n_out;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, s));
-  __syncwarp();
-  for (int k0 = 0; k0 < n_max; k0 += P_CHUNK) {
-    if (k0 < n_out) {
-#pragma unroll 8
-      for (int j = 0; j < P_CHUNK; j++) {
-        tile[lane][j] = p;           // phase of output k0 + j
-        p = cmul_unfused(p, inc);    // src/xlating.c:71
-      }
-      // the recursion ran past n_out inside the last chunk: rewind is not possible,
-      // so the final phase is re-derived below from the stored tile
-    }
-    __syncwarp();
-    for (int r = 0; r < 32; r++) {
-      const int k = k0 + lane;
-      if (k < s_n[r]) phases[s_off[r] + k] = tile[r][lane];
-    }
-    __syncwarp();
-    if (k0 < n_out && k0 + P_CHUNK > n_out) {
-      // exact phase after the last output: phase of output n_out-1 advanced once
-      p = cmul_unfused(tile[lane][n_out - 1 - k0], inc);
-    }
-  }
-  if (!live) return;
   if (n_out > 0 && d->renorm) {
     // src/xlating.c:73.  glibc's hypotf is (float)sqrt((double)x*x + (double)y*y)
     // (verified on 5e7 random inputs); the products are exact in double.
@@ -211,7 +190,7 @@ phase_cf32_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict
   d->hist = (S + n_in) - (first + (long long)n_out * D);  // src/xlating.c:76
 }
 
-__global__ void __launch_bounds__(P_THREADS)
+__global__ void __launch_bounds__(P_QTHREADS)
 phase_q15_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict__ blk,
                  short2 *__restrict__ qphases, long long S, int n_in) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,7 +282,7 @@ fir_generic_cf32_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restr
     if (lane == i) mine = acc[i];
   const int k = k0 + lane;
   if (lane < G_OPW && k < b.n_out) {
-    const float2 ph = phases[d->out_off + k];
+    const float2 ph = phases[d->ph_off + (size_t)k * 32];
     out[d->out_off + k] = cmul_unfused(mine, ph);  // src/xlating.c:70
   }
 }
@@ -400,8 +379,9 @@ struct TileClass {
   int tiles;           // ceil(n_out / 128)
   int cta_begin;       // first CTA of this class in the launch
   int members_off;     // into the members table: client index or -1, 32 per group
-  int xs_len;          // float2 in the input tile: (T_KT-1)*Dp + L
-  int pad_;
+  int xs_len;          // float2 in the input tile: (KT-1)*Dp + L
+  int ph_stride;       // float2 between the oscillator tables of consecutive client groups
+  long long ph_base;   // float2 offset of (group 0, output 0, lane 0) in the oscillator table
 };
 
 struct TileLaunch {
@@ -588,21 +568,226 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   }
 
   // epilogue: derotate with the pre-computed oscillator and store (coalesced in k).
-  // All loads of one client are issued before their first use.
+  // The oscillator table is [k][32 clients]: this thread's 8 clients are 64
+  // contiguous bytes per output.  All loads are issued before their first use.
   if (warp_active) {
+    const float4 *pt = reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride + warp * T_RC);
 #pragma unroll
-    for (int c = 0; c < T_RC; c++) {
-      if (off[c] < 0) continue;
-      float2 ph[T_RK];
+    for (int i = 0; i < T_RK; i++) {
+      const int k = k0 + lane + 32 * i;
+      if (k >= n_out) continue;
+      float4 ph[T_RC / 2];
 #pragma unroll
-      for (int i = 0; i < T_RK; i++) {
-        const int k = k0 + lane + 32 * i;
-        ph[i] = (k < n_out) ? __ldg(phases + off[c] + k) : make_float2(0.f, 0.f);
+      for (int q = 0; q < T_RC / 2; q++) ph[q] = __ldg(pt + (size_t)k * 16 + q);
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++) {
+        if (off[2 * q] >= 0)
+          out[off[2 * q] + k] = cmul_unfused(acc[i][2 * q], make_float2(ph[q].x, ph[q].y));  // src/xlating.c:70
+        if (off[2 * q + 1] >= 0)
+          out[off[2 * q + 1] + k] = cmul_unfused(acc[i][2 * q + 1], make_float2(ph[q].z, ph[q].w));
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tiled multi-client FIR, packed-FMA version (fma.rn.f32x2 -> SASS FFMA2)
+//
+// The FP32 pipe retires 128 FMA/clk/SM either as 4 scalar FFMA or as 2 packed FFMA2
+// per scheduler and clock; packed math halves the issue slots the FMAs need, which
+// leaves room for the shared-memory loads (and for co-resident kernels such as the
+// oscillator pre-pass) without starving the pipe.  To use packed operands with no
+// per-tap shuffling the complex MAC is split into two real-scaled sums,
+//     A1 += (xr, xi) * (tr, tr)        A2 += (xr, xi) * (ti, ti)
+//     re = A1.x - A2.y                 im = A1.y + A2.x          (once, at the end)
+// so x comes straight out of a 64-bit shared load and the taps are stored in
+// shared memory as (tr, tr, ti, ti): one 128-bit load yields both packed operands.
+//
+// CTA = 4 warps = 32 clients x 64 outputs.  In a warp, lane = (h, o): o = lane&15
+// selects the output column, h = lane>>4 the client half; thread tile 4 outputs
+// (o + 16 i) x 4 clients (4h + q).  The two half-warps read the same x (broadcast)
+// and two different 16-byte tap segments, so every shared load is ONE wavefront.
+// ---------------------------------------------------------------------------
+constexpr int U_THREADS = 128;
+constexpr int U_WARPS = 4;
+constexpr int U_RK = 4;
+constexpr int U_RC = 4;
+constexpr int U_KT = 16 * U_RK;          // 64 outputs per CTA
+constexpr int U_CG = U_WARPS * 2 * U_RC; // 32 clients per CTA
+constexpr int U_JC = 16;                 // flat taps per TMA chunk
+constexpr int U_STAGES = 3;
+constexpr int U_CHUNK_BYTES = U_JC * U_CG * 16;  // 8 KiB: (tr,tr,ti,ti) per client-tap
+constexpr int U_SMEM_FIXED = U_STAGES * U_CHUNK_BYTES + 64;
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+__global__ void __launch_bounds__(U_THREADS, 4)
+fir_tile2_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
+                      const float4 *__restrict__ tile_taps, const int *__restrict__ member_off,
+                      const float2 *__restrict__ phases, float2 *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  ulonglong2 *ts = reinterpret_cast<ulonglong2 *>(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + U_STAGES * U_CHUNK_BYTES);
+  float2 *xs = reinterpret_cast<float2 *>(smem + U_SMEM_FIXED);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o = lane & 15, h = lane >> 4;
+
+  int ci = 0;
+  while (ci + 1 < P.n_classes && (int)blockIdx.x >= P.cls[ci + 1].cta_begin) ci++;
+  const TileClass &K = P.cls[ci];
+  const int local = (int)blockIdx.x - K.cta_begin;
+  const int grp = local / K.tiles;
+  const int tile = local - grp * K.tiles;
+  const int k0 = tile * U_KT;
+  const int D = K.D, Dp = K.Dp, L = K.L;
+  const int n_out = K.n_out;
+  const int nchunks = (L + U_JC - 1) / U_JC;
+
+  if (tid == 0) {
+    for (int s = 0; s < U_STAGES; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // taps of this client group: [flat tap][32 clients] x 16 B
+  const float4 *gt = tile_taps + K.taps_off + (long long)grp * L * U_CG;
+  if (tid == 0) {
+    for (int s = 0; s < U_STAGES && s < nchunks; s++) {
+      const unsigned bytes = (unsigned)min(U_JC, L - s * U_JC) * U_CG * 16u;
+      mbar_expect_tx(&bars[s], bytes);
+      tma_bulk_g2s(ts + s * (U_JC * U_CG), gt + (long long)s * (U_JC * U_CG), bytes, &bars[s]);
+    }
+  }
+
+  // input tile, skewed layout (see TileClass): coalesced 8-byte cp.async
+  {
+    const long long w0 = K.first + (long long)k0 * D;
+    int row = tid / Dp, col = tid - row * Dp;
+    const int drow = U_THREADS / Dp, dcol = U_THREADS - drow * Dp;
+    for (int e = tid; e < K.xs_len; e += U_THREADS) {
+      if (col < D) {
+        const long long ab = w0 + (long long)row * D + col;
+        cp_async_8(xs + e, ring + ((unsigned)((unsigned long long)ab) & mask));
+      } else {
+        xs[e] = make_float2(0.f, 0.f);
+      }
+      row += drow;
+      col += dcol;
+      if (col >= Dp) {
+        col -= Dp;
+        row++;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  int off[U_RC];
+  {
+    const int *mo = member_off + K.members_off + grp * U_CG + warp * (2 * U_RC) + h * U_RC;
 #pragma unroll
-      for (int i = 0; i < T_RK; i++) {
-        const int k = k0 + lane + 32 * i;
-        if (k < n_out) out[off[c] + k] = cmul_unfused(acc[i][c], ph[i]);  // src/xlating.c:70
+    for (int q = 0; q < U_RC; q++) off[q] = __ldg(mo + q);
+  }
+  // members are packed from the front of a group: a warp whose first client is a
+  // padding slot has nothing to do
+  const bool warp_active = __shfl_sync(0xffffffffu, off[0], 0) >= 0;
+
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  u64 A1[U_RK][U_RC], A2[U_RK][U_RC];
+#pragma unroll
+  for (int i = 0; i < U_RK; i++)
+#pragma unroll
+    for (int q = 0; q < U_RC; q++) A1[i][q] = A2[i][q] = 0ull;
+
+  const u64 *xq = reinterpret_cast<const u64 *>(xs);
+  const u64 *xb0 = xq + o * Dp;
+  const u64 *xb1 = xb0 + 16 * Dp;
+  const u64 *xb2 = xb1 + 16 * Dp;
+  const u64 *xb3 = xb2 + 16 * Dp;
+
+  for (int ch = 0; ch < nchunks; ch++) {
+    const int s = ch % U_STAGES;
+    mbar_wait(&bars[s], (unsigned)((ch / U_STAGES) & 1));
+    if (warp_active) {
+      const int len = min(U_JC, L - ch * U_JC);
+      const ulonglong2 *tp = ts + s * (U_JC * U_CG) + warp * (2 * U_RC) + h * U_RC;
+      const int fbase = ch * U_JC;
+      u64 xn[U_RK];
+      ulonglong2 tn[U_RC];
+      xn[0] = xb0[fbase];
+      xn[1] = xb1[fbase];
+      xn[2] = xb2[fbase];
+      xn[3] = xb3[fbase];
+#pragma unroll
+      for (int q = 0; q < U_RC; q++) tn[q] = tp[q];
+#pragma unroll 1
+      for (int f = 0; f < len; f += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          u64 x[U_RK];
+          ulonglong2 t[U_RC];
+#pragma unroll
+          for (int i = 0; i < U_RK; i++) x[i] = xn[i];
+#pragma unroll
+          for (int q = 0; q < U_RC; q++) t[q] = tn[q];
+          const int fn = f + u + 1;  // one tap ahead; the read past a chunk is discarded
+          xn[0] = xb0[fbase + fn];
+          xn[1] = xb1[fbase + fn];
+          xn[2] = xb2[fbase + fn];
+          xn[3] = xb3[fbase + fn];
+#pragma unroll
+          for (int q = 0; q < U_RC; q++) tn[q] = tp[fn * U_CG + q];
+#pragma unroll
+          for (int i = 0; i < U_RK; i++) {
+#pragma unroll
+            for (int q = 0; q < U_RC; q++) {
+              A1[i][q] = ffma2(x[i], t[q].x, A1[i][q]);
+              A2[i][q] = ffma2(x[i], t[q].y, A2[i][q]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && ch + U_STAGES < nchunks) {
+      const int nx = ch + U_STAGES;
+      const unsigned bytes = (unsigned)min(U_JC, L - nx * U_JC) * U_CG * 16u;
+      mbar_expect_tx(&bars[s], bytes);
+      tma_bulk_g2s(ts + s * (U_JC * U_CG), gt + (long long)nx * (U_JC * U_CG), bytes, &bars[s]);
+    }
+  }
+
+  if (warp_active) {
+    const float4 *pt = reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride +
+                                                        warp * (2 * U_RC) + h * U_RC);
+#pragma unroll
+    for (int i = 0; i < U_RK; i++) {
+      const int k = k0 + o + 16 * i;
+      if (k >= n_out) continue;
+      float4 ph[U_RC / 2];
+#pragma unroll
+      for (int q = 0; q < U_RC / 2; q++) ph[q] = __ldg(pt + (size_t)k * 16 + q);
+#pragma unroll
+      for (int q = 0; q < U_RC; q++) {
+        if (off[q] < 0) continue;
+        const float2 a1 = unpack2(A1[i][q]), a2 = unpack2(A2[i][q]);
+        const float2 acc = make_float2(a1.x - a2.y, a1.y + a2.x);
+        const float2 pq = (q & 1) ? make_float2(ph[q / 2].z, ph[q / 2].w) : make_float2(ph[q / 2].x, ph[q / 2].y);
+        out[off[q] + k] = cmul_unfused(acc, pq);  // src/xlating.c:70
       }
     }
   }
