@@ -206,12 +206,34 @@ def cpu_arm(wl, budget_s, flavor=None):
 
 
 # ---------------------------------------------------------------------------
-# main
+# multi-GPU plumbing (one process per GPU, one independent stream per GPU; the only
+# collectives are the barrier and the max-over-ranks of the timed region)
 # ---------------------------------------------------------------------------
+def stream_seed(rank):
+    """Each rank decimates its OWN wideband stream (weak scaling)."""
+    return 1000 + rank
+
+
+def max_over_ranks(x, world, device=None):
+    """MAX all-reduce of a python float (NCCL on GPU boxes, gloo in the CPU tests)."""
+    if world <= 1:
+        return float(x)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def job_throughput_msps(block_samples, steps, world, elapsed_ms_max):
+    """Whole-job input MS/s: every rank pushed `steps` blocks of its own stream."""
+    return world * block_samples * steps / (elapsed_ms_max * 1e-3) / 1e6
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
@@ -219,6 +241,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-partition", action="store_true",
+                    help="do not reserve 8 SMs (green context) for the oscillator pre-pass")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -274,13 +298,16 @@ def main():
 
     fmt_code = pkg.FMT[wl["fmt"]]
     n_dev_blocks = 512
-    host_blocks = synth_blocks(wl["fmt"], n_dev_blocks, wl["block_elems"], seed=1000 + rank)
+    host_blocks = synth_blocks(wl["fmt"], n_dev_blocks, wl["block_elems"], seed=stream_seed(rank))
     dev = torch.from_numpy(host_blocks.view(np.uint8).reshape(n_dev_blocks, -1)).cuda()
     blk_stride = dev.stride(0)
     base_ptr = dev.data_ptr()
 
     # ---- tier (i): inputs resident in HBM, outputs stay in HBM -> `value`
-    g, ids, taplens = build_group(pkg.XLG_OUT_DEVICE)
+    part_flag = 0 if args.no_partition else pkg.XLG_SM_PARTITION
+    config["sm_partition"] = ("off" if args.no_partition else
+                              "8 SMs reserved for the oscillator pre-pass, FIR on the other 140 (CUDA green contexts)")
+    g, ids, taplens = build_group(pkg.XLG_OUT_DEVICE | part_flag)
     config["taps_len"] = sorted(set(taplens.values()))
     step_no = [0]
 
@@ -292,34 +319,32 @@ def main():
             last = g.submit_ptr(fmt_code, base_ptr + b * blk_stride, wl["block_elems"], pkg.XLG_INPUT_DEVICE)
         return last
 
-    g.wait(run_steps(args.warmup))
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # samples through warm-up, the timed region, the per-kernel pass and e2e
+    g.wait(run_steps(args.warmup))
+    g.profile_read(reset=True)
     barrier()
     g.timer_start()
     last = run_steps(args.steps)
     ms = g.timer_stop()
+    host = g.profile_read(reset=True)
     barrier()
     g.wait(last)
     # per-kernel pass (CUDA events around every launch, on the launching stream)
     g.profile_enable(True)
     g.profile_read(reset=True)
-    last = run_steps(args.steps)
+    last = run_steps(min(args.steps, 400))
     g.wait(last)
     g.profile_enable(False)
     prof = g.profile_read(reset=True)
-    clocks = sampler.stop() if rank == 0 else None
     n_out_total = sum(g.output_ptr(last, c)[1] for c in ids)
     kinds = sorted({g.client_info(c)[1] for c in ids})
     g.close()
 
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms, world, "cuda")
     ms_per_step = ms_max / args.steps
-    value = world * wl["block_samples"] * args.steps / (ms_max * 1e-3) / 1e6
+    value = job_throughput_msps(wl["block_samples"], args.steps, world, ms_max)
 
     # ---- tier (iii): through the C ABI with host buffers -> `e2e`
     e2e = None
@@ -344,24 +369,22 @@ def main():
                 g2.wait(tk)
 
         run_e2e(args.warmup)
-        e2e_steps = min(args.steps, 200)
+        e2e_steps = min(args.steps, 400)
         barrier()
         t0 = time.perf_counter()
         run_e2e(e2e_steps)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         barrier()
-        tw_ = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tw_, op=dist.ReduceOp.MAX)
-        wall = float(tw_.item())
-        e2e = {"value": world * wl["block_samples"] * e2e_steps / wall / 1e6, "unit": "MS/s",
+        wall = max_over_ranks(wall, world, "cuda")
+        e2e = {"value": job_throughput_msps(wl["block_samples"], e2e_steps, world, wall * 1e3), "unit": "MS/s",
                "h2d_bytes_per_step": BLOCK_BYTES, "d2h_bytes_per_step": int(n_out_total * 8),
                "steps": e2e_steps, "timing": "host wall clock around submit..wait of every block (pinned host buffers)"}
         g2.close()
         for p in pins:
             p.free()
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,7 +399,13 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     algo_bytes = BLOCK_BYTES + 8 * n_out_total  # read the block once, write cf32 per client
-    roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(args.workload + ":" + args.taps, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": traffic,
             "peak_source": peak_src, "kernel": "fir_tile_cf32_kernel", "algorithmic_bytes_per_launch": algo_bytes}
     fp32 = None
     if prof["fir_tile_launches"] > 0:
@@ -397,7 +426,13 @@ def main():
         fp32 = {"bound": "fp32_fma", "achieved": algo_fma / (k_ms * 1e-3) / 1e12, "issued": issued_fma / (k_ms * 1e-3) / 1e12,
                 "peak": fp32_peak, "unit": "TFMA/s", "frac": algo_fma / (k_ms * 1e-3) / 1e12 / fp32_peak,
                 "peak_source": fp32_src,
-                "note": "this path is bound by the FP32 FMA pipe, not HBM (DESIGN.md section 4)"}
+                "steady_state": {"ms_per_step": ms_max / args.steps,
+                                 "achieved": algo_fma / (ms_max / args.steps * 1e-3) / 1e12,
+                                 "frac": algo_fma / (ms_max / args.steps * 1e-3) / 1e12 / fp32_peak,
+                                 "note": "whole pipelined step (consecutive blocks overlap on two streams); a lower "
+                                         "bound for the kernel, the step may be bound by the oscillator pre-pass"},
+                "note": "this path is bound by the FP32 FMA pipe, not HBM (DESIGN.md section 4); kernel_ms is the "
+                        "kernel alone (non-overlapped pass, CUDA events on its stream)"}
         roof["fp32"] = fp32
     roof["step_kernels_ms"] = {"convert": prof["convert_ms"] / max(prof["convert_launches"], 1),
                                "phase": prof["phase_ms"] / max(prof["phase_launches"], 1),
@@ -411,7 +446,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "client_msps": value * len(wl["plan"]),
             "realtime_clients_per_gpu": int(value / world * len(wl["plan"]) * 1e6 / wl["fs"]),
-            "kernels_used": kinds, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "kernels_used": kinds, "clocks": clocks,
+            "host": {"submit_us_per_step": 1e3 * host["host_submit_ms"] / max(host["submits"], 1),
+                     "of_which_waiting_for_gpu_us": 1e3 * host["host_wait_ms"] / max(host["submits"], 1)}, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roof}
     if not args.no_cpu and world == 1:
         try:

@@ -111,6 +111,10 @@ typedef struct {
   uint64_t in_samples;   /* complex inputs consumed */
   uint64_t tile_macs;    /* complex MACs issued by the tiled kernel incl. padding */
   uint64_t algo_macs;    /* algorithmic complex MACs: sum n_out * taps_len */
+  /* host side of xlg_submit (always counted, also with profiling off) */
+  double host_submit_ms; /* wall time spent inside xlg_submit, including ...          */
+  double host_wait_ms;   /* ... the part spent waiting for a free slot (GPU is behind) */
+  uint64_t submits;
 } xlg_profile;
 int xlg_profile_enable(xlg_group *g, int on);
 int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset);

@@ -57,7 +57,8 @@ class XlgProfile(C.Structure):
                 ("convert_ms", C.c_double), ("fir_tile_launches", C.c_uint64),
                 ("fir_generic_launches", C.c_uint64), ("phase_launches", C.c_uint64),
                 ("convert_launches", C.c_uint64), ("blocks", C.c_uint64), ("out_samples", C.c_uint64),
-                ("in_samples", C.c_uint64), ("tile_macs", C.c_uint64), ("algo_macs", C.c_uint64)]
+                ("in_samples", C.c_uint64), ("tile_macs", C.c_uint64), ("algo_macs", C.c_uint64),
+                ("host_submit_ms", C.c_double), ("host_wait_ms", C.c_double), ("submits", C.c_uint64)]
 
 
 def build(verbose: bool = False) -> None:

@@ -183,6 +183,81 @@ __global__ void __launch_bounds__(128, 4) k_v2(float *out, int passes, long long
   if (tid == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// ---- variant 3: packed FFMA2 over PAIRS OF OUTPUTS, 4 outputs x 8 clients ----
+// lane = output column (as v1).  x tile stored as two planes (re, im): the two
+// 32-bit loads of outputs (i0, i1) land in one register pair, so no shuffling.
+// taps stored (tr, tr, ti, ti) per client-tap.  Per (pair P, client c):
+//   RE_P += XR_P*(tr,tr) + XIn_P*(ti,ti);   IM_P += XR_P*(ti,ti) + XI_P*(tr,tr)
+// with XIn_P = -XI_P (two LOP3 per pair and tap).
+__device__ __forceinline__ u64 pack2f(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__global__ void __launch_bounds__(128, 3) k_v3(float *out, int passes, long long *cycles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  ulonglong2 *ts = reinterpret_cast<ulonglong2 *>(smem);             // [LFLAT][32] x 16 B
+  float *xr = reinterpret_cast<float *>(smem + LFLAT * 32 * 16);
+  const int xs_len = 127 * DP + LFLAT + 8;
+  float *xi = xr + xs_len;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float4 *tf = reinterpret_cast<float4 *>(ts);
+  for (int i = tid; i < LFLAT * 32; i += 128) {
+    float a = 0.001f * (i % 13), b = 0.002f * (i % 7);
+    tf[i] = make_float4(a, a, b, b);
+  }
+  for (int i = tid; i < xs_len; i += 128) {
+    xr[i] = 0.01f * (i % 11);
+    xi[i] = 0.02f * (i % 5);
+  }
+  __syncthreads();
+  u64 RE[2][8], IM[2][8];
+  for (int pz = 0; pz < 2; pz++)
+    for (int c = 0; c < 8; c++) RE[pz][c] = IM[pz][c] = 0ull;
+  const float *r0 = xr + lane * DP, *r1 = r0 + 32 * DP, *r2 = r1 + 32 * DP, *r3 = r2 + 32 * DP;
+  const float *i0 = xi + lane * DP, *i1 = i0 + 32 * DP, *i2 = i1 + 32 * DP, *i3 = i2 + 32 * DP;
+  const ulonglong2 *tp = ts + warp * 8;
+  long long t0 = clock64();
+  for (int p = 0; p < passes; p++) {
+#pragma unroll 1
+    for (int f = 0; f < LFLAT; f += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const float a0 = r0[f + u], a1 = r1[f + u], a2 = r2[f + u], a3 = r3[f + u];
+        const float b0 = i0[f + u], b1 = i1[f + u], b2 = i2[f + u], b3 = i3[f + u];
+        u64 XR[2], XI[2], XN[2];
+        XR[0] = pack2f(a0, a1);
+        XR[1] = pack2f(a2, a3);
+        XI[0] = pack2f(b0, b1);
+        XI[1] = pack2f(b2, b3);
+        XN[0] = XI[0] ^ 0x8000000080000000ull;
+        XN[1] = XI[1] ^ 0x8000000080000000ull;
+        ulonglong2 t[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) t[c] = tp[(f + u) * 32 + c];
+#pragma unroll
+        for (int pz = 0; pz < 2; pz++)
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            RE[pz][c] = ffma2(XR[pz], t[c].x, RE[pz][c]);
+            RE[pz][c] = ffma2(XN[pz], t[c].y, RE[pz][c]);
+            IM[pz][c] = ffma2(XR[pz], t[c].y, IM[pz][c]);
+            IM[pz][c] = ffma2(XI[pz], t[c].x, IM[pz][c]);
+          }
+      }
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+  for (int pz = 0; pz < 2; pz++)
+    for (int c = 0; c < 8; c++) {
+      float2 a = unpack2(RE[pz][c]), b = unpack2(IM[pz][c]);
+      s += a.x + a.y + b.x + b.y;
+    }
+  out[blockIdx.x * 128 + tid] = s;
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 template <typename K>
 static void run(const char *name, K kernel, int per_sm, size_t smem, int passes, double fma_per_thread_pass,
                 float *d_out, long long *d_cyc, int sms) {
@@ -223,11 +298,13 @@ int main(int argc, char **argv) {
   cudaMalloc(&d_cyc, sizeof(long long) * 148 * 8);
   const size_t smem1 = (size_t)LFLAT * 32 * 8 + (127 * DP + LFLAT + 8) * 8;   // 131 KB + 48 KB
   const size_t smem2 = (size_t)LFLAT * 32 * 16 + (63 * DP + LFLAT + 8) * 8;
-  printf("{\"smem_v1\": %zu, \"smem_v2\": %zu}\n", smem1, smem2);
+  const size_t smem3 = (size_t)LFLAT * 32 * 16 + (127 * DP + LFLAT + 8) * 8;
+  printf("{\"smem_v1\": %zu, \"smem_v2\": %zu, \"smem_v3\": %zu}\n", smem1, smem2, smem3);
   for (int per_sm = 1; per_sm <= 3; per_sm++) {
     run("v1_ffma_4x8", k_v1<0>, per_sm, smem1, passes, LFLAT * 128.0, d_out, d_cyc, sms);
     run("v2_ffma2_4x4_plain", k_v2<0>, per_sm, smem2, passes, LFLAT * 64.0, d_out, d_cyc, sms);
     run("v2_ffma2_4x4_pingpong", k_v2<1>, per_sm, smem2, passes, LFLAT * 64.0, d_out, d_cyc, sms);
+    run("v3_ffma2_pairs_4x8", k_v3, per_sm, smem3, passes, LFLAT * 128.0, d_out, d_cyc, sms);
   }
   return 0;
 }

@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -184,6 +185,7 @@ struct xlg_group {
 
   bool profiling = false;
   xlg_profile prof;
+  uint64_t host_submit_ns = 0, host_wait_ns = 0, host_count_base = 0;
   std::mutex mu;  // guards slots' harvest + profile
 };
 
@@ -861,8 +863,11 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
 
   const int64_t ticket = g->next_ticket;
   Slot &s = g->slots[ticket % XLG_SLOTS];
+  const auto t_enter = std::chrono::steady_clock::now();
   if (s.ticket >= 0) {
     CU_OK(cudaEventSynchronize(s.ev_done));
+    g->host_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                           std::chrono::steady_clock::now() - t_enter).count();
     std::lock_guard<std::mutex> lk(g->mu);
     harvest_locked(g, s);
   }
@@ -1040,6 +1045,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   s.ticket = ticket;
   s.harvested = false;
   g->next_ticket++;
+  g->host_submit_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                           std::chrono::steady_clock::now() - t_enter).count();
   return ticket;
 }
 
@@ -1142,6 +1149,13 @@ extern "C" int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset) {
   if (g == nullptr || p == nullptr) return -EINVAL;
   std::lock_guard<std::mutex> lk(g->mu);
   *p = g->prof;
-  if (reset) memset(&g->prof, 0, sizeof(g->prof));
+  p->host_submit_ms = (double)g->host_submit_ns * 1e-6;
+  p->host_wait_ms = (double)g->host_wait_ns * 1e-6;
+  p->submits = (uint64_t)g->next_ticket - g->host_count_base;
+  if (reset) {
+    memset(&g->prof, 0, sizeof(g->prof));
+    g->host_submit_ns = g->host_wait_ns = 0;
+    g->host_count_base = (uint64_t)g->next_ticket;
+  }
   return 0;
 }
