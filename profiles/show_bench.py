@@ -1,7 +1,12 @@
-import json,sys
+import json, sys
 for f in sys.argv[1:]:
     try:
-        d=json.load(open(f))
-        print(f, "value=%.1f ms/step=%.4f e2e=%s fp32frac=%.3f kern=%s"%(d["value"], d["ms_per_step"], (d.get("e2e") or {}).get("value"), d["roofline"]["fp32"]["frac"], {k:round(v,4) for k,v in d["roofline"]["step_kernels_ms"].items()}))
+        d = json.load(open(f))
+        r = d["roofline"]
+        print(f, "value=%.1f ms/step=%.4f e2e=%s fp32frac=%.3f steady=%.3f kern=%s host=%s clocks=%s" % (
+            d["value"], d["ms_per_step"], (d.get("e2e") or {}).get("value"), r["fp32"]["frac"],
+            r["fp32"].get("steady_state", {}).get("frac", 0),
+            {k: round(v, 4) for k, v in r["step_kernels_ms"].items()},
+            {k: round(v, 1) for k, v in d.get("host", {}).items()}, d.get("clocks")))
     except Exception as e:
         print(f, "ERR", e)

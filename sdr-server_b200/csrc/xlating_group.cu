@@ -163,7 +163,7 @@ struct xlg_group {
   float2 *d_taps = nullptr;
   short2 *d_qtaps = nullptr;
   void *d_tile_taps = nullptr;
-  int tile_ver = 1;       // 1 = scalar-FFMA tile kernel (faster, default), 2 = packed FFMA2 tile kernel
+  int tile_lo = 32;       // output lanes per warp in the tiled kernel: 32 (128-output tiles) or 16 (64)
   int *d_members = nullptr;
   int *d_order = nullptr;   // clients in oscillator-table order, 32 per group, -1 = padding
   int n_order = 0;
@@ -408,9 +408,8 @@ static int rebuild_layout(xlg_group *g) {
   }
   std::vector<int> members;
   std::vector<float2> tile_taps;  // v1: one float2 per client-tap; v2: two (tr,tr),(ti,ti)
-  const int KT = g->tile_ver == 2 ? U_KT : T_KT;
-  const int per_tap = g->tile_ver == 2 ? 2 : 1;
-  const size_t smem_fixed = g->tile_ver == 2 ? (size_t)U_SMEM_FIXED : (size_t)T_SMEM_FIXED;
+  const int KT = g->tile_lo * T_RK;
+  const size_t smem_fixed = (size_t)T_SMEM_FIXED;
   for (auto &kv : buckets) {
     const uint32_t D = std::get<0>(kv.first);
     const size_t T = std::get<1>(kv.first);
@@ -433,11 +432,12 @@ static int rebuild_layout(xlg_group *g) {
     ch.k.L = L;
     ch.k.xs_len = xs_len;
     ch.k.n_groups = (int)((ids.size() + T_CG - 1) / T_CG);
+    ch.k.n_members = (int)ids.size();
     ch.k.members_off = (int)members.size();
-    ch.k.taps_off = (long long)(tile_taps.size() / per_tap);
+    ch.k.taps_off = (long long)tile_taps.size();
     for (int gi = 0; gi < ch.k.n_groups; gi++) {
       const size_t base = tile_taps.size();
-      tile_taps.resize(base + (size_t)L * T_CG * per_tap, make_float2(0.f, 0.f));
+      tile_taps.resize(base + (size_t)L * T_CG, make_float2(0.f, 0.f));
       for (int m = 0; m < T_CG; m++) {
         const size_t idx = (size_t)gi * T_CG + m;
         if (idx >= ids.size()) {
@@ -450,12 +450,7 @@ static int rebuild_layout(xlg_group *g) {
         const HostClient &h = g->clients[id];
         for (size_t j = 0; j < T; j++) {
           const size_t f = (j / D) * Dp + (j % D);
-          if (per_tap == 1) {
-            tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
-          } else {
-            tile_taps[base + (f * T_CG + m) * 2] = make_float2(h.rev[2 * j], h.rev[2 * j]);
-            tile_taps[base + (f * T_CG + m) * 2 + 1] = make_float2(h.rev[2 * j + 1], h.rev[2 * j + 1]);
-          }
+          tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
         }
       }
     }
@@ -695,11 +690,11 @@ extern "C" int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input
   // the tiled kernel needs > 48 KiB of dynamic shared memory
   {
     const char *tv = getenv("XLATING_B200_TILE");
-    if (tv != nullptr && atoi(tv) == 2) g->tile_ver = 2;
+    if (tv != nullptr && atoi(tv) == 16) g->tile_lo = 16;
   }
-  if (cudaFuncSetAttribute(fir_tile_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+  if (cudaFuncSetAttribute(fir_tile_cf32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(fir_tile2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
@@ -980,12 +975,11 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       // hist was already advanced above; recover this block's window start
       k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
       k.n_out = n_out;
-      const int KT = g->tile_ver == 2 ? U_KT : T_KT;
+      const int KT = g->tile_lo * T_RK;
       k.tiles = (n_out + KT - 1) / KT;
       k.cta_begin = ctas;
       ctas += k.tiles * k.n_groups;
-      smem = std::max(smem, (size_t)(g->tile_ver == 2 ? U_SMEM_FIXED : T_SMEM_FIXED) +
-                                ((size_t)k.xs_len + 8) * sizeof(float2));
+      smem = std::max(smem, (size_t)T_SMEM_FIXED + ((size_t)k.xs_len + 8) * sizeof(float2));
       P.cls[P.n_classes++] = k;
       s.tile_macs += (uint64_t)k.tiles * KT * (uint64_t)k.L * (uint64_t)ch.members.size();
     }
@@ -994,12 +988,12 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
         CU_OK(cudaEventRecord(s.pf[4], cs));
         s.pf_tile = true;
       }
-      if (g->tile_ver == 2)
-        fir_tile2_cf32_kernel<<<ctas, U_THREADS, smem, cs>>>(P, g->ring, mask, (const float4 *)g->d_tile_taps,
-                                                            g->d_members, s.d_phases, s.d_out);
+      if (g->tile_lo == 16)
+        fir_tile_cf32_kernel<16><<<ctas, TileShape<16>::kThreads, smem, cs>>>(
+            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out);
       else
-        fir_tile_cf32_kernel<<<ctas, T_THREADS, smem, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
-                                                           g->d_members, s.d_phases, s.d_out);
+        fir_tile_cf32_kernel<32><<<ctas, TileShape<32>::kThreads, smem, cs>>>(
+            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out);
       if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], cs));
     }
   }

@@ -18,7 +18,7 @@
  *                    block instead of once per client
  *   phase_*          the reference's sequential float (or Q15) oscillator, one
  *                    thread per client, bit-exact (unfused mul/add, exact hypotf)
- *   fir_tile_cf32    the dominant kernel: 32 clients x 128 outputs per CTA,
+ *   fir_tile_cf32    the dominant kernel: 32 clients x 64 (or 128) outputs per CTA,
  *                    4 outputs x 8 clients per thread in registers, input tile
  *                    staged with coalesced 8-byte cp.async into a bank-conflict-
  *                    free skewed layout, taps streamed by TMA bulk copies
@@ -352,18 +352,38 @@ fir_generic_q15_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restri
 // ---------------------------------------------------------------------------
 // tiled multi-client FIR (the dominant kernel)
 // ---------------------------------------------------------------------------
-constexpr int T_THREADS = 128;
-constexpr int T_WARPS = T_THREADS / 32;
-constexpr int T_RK = 4;              // outputs per thread (k = k0 + lane + 32*i)
+constexpr int T_RK = 4;              // outputs per thread
 constexpr int T_RC = 8;              // clients per thread
-constexpr int T_KT = 32 * T_RK;      // 128 outputs per CTA
-constexpr int T_CG = T_WARPS * T_RC; // 32 clients per CTA
+constexpr int T_CG = 32;             // clients per CTA
 constexpr int T_JC = 32;             // flat taps per TMA chunk
 constexpr int T_STAGES = 3;
+#ifndef XL_TILE_UNROLL
+#define XL_TILE_UNROLL 8
+#endif
+constexpr int T_UNROLL = XL_TILE_UNROLL;  // taps per unrolled inner-loop body (L is a multiple of 8)
 constexpr int T_CHUNK_F2 = T_JC * T_CG;       // float2 per chunk (1024)
 constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
 constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
 constexpr int T_MAX_CLASSES = 8;
+
+// Lane mapping of a warp, LO = number of output lanes:
+//   LO = 32: lane = output column; the warp covers 128 outputs x 8 clients, the CTA
+//            (4 warps) 128 outputs x 32 clients.
+//   LO = 16: lane = (h, o), o = lane & 15 the output column, h = lane >> 4 the client
+//            half; the warp covers 64 outputs x 16 clients, the CTA (2 warps)
+//            64 outputs x 32 clients.  Both half-warps read the same x (one shared-
+//            memory wavefront instead of two) and tiles are half as large, which
+//            gives the block scheduler twice as many, smaller CTAs to balance.
+// The thread tile is 4 outputs x 8 clients in both cases.
+template <int LO>
+struct TileShape {
+  static constexpr int kHalves = 32 / LO;                    // client halves per warp
+  static constexpr int kWarpClients = kHalves * T_RC;        // 8 or 16
+  static constexpr int kWarps = T_CG / kWarpClients;         // 4 or 2
+  static constexpr int kThreads = kWarps * 32;               // 128 or 64
+  static constexpr int kKT = LO * T_RK;                      // 128 or 64 outputs per CTA
+  static constexpr int kMinCtas = LO == 32 ? 3 : 6;          // register budget hint
+};
 
 // One class = clients with identical (D, T, window alignment).  "Flat" tap index:
 // tap j = q*D + r lives at f = q*Dp + r with Dp = D rounded up to odd, so that a
@@ -376,11 +396,13 @@ struct TileClass {
   int n_out;
   int D, Dp, L;        // L = flat length, multiple of 8
   int n_groups;        // CTA groups of 32 clients
-  int tiles;           // ceil(n_out / 128)
+  int tiles;           // ceil(n_out / KT)
   int cta_begin;       // first CTA of this class in the launch
-  int members_off;     // into the members table: client index or -1, 32 per group
+  int members_off;     // into the member table: output row offset or -1, 32 per group
   int xs_len;          // float2 in the input tile: (KT-1)*Dp + L
   int ph_stride;       // float2 between the oscillator tables of consecutive client groups
+  int n_members;       // real clients in the class (the last group may be partly padding)
+  int pad_;
   long long ph_base;   // float2 offset of (group 0, output 0, lane 0) in the oscillator table
 };
 
@@ -395,6 +417,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
   asm volatile(
@@ -420,16 +445,23 @@ __device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(T_THREADS, 3)
+template <int LO>
+__global__ void __launch_bounds__(TileShape<LO>::kThreads, TileShape<LO>::kMinCtas)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
                      const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
                      const float2 *__restrict__ phases, float2 *__restrict__ out) {
+  using S = TileShape<LO>;
+  constexpr int NT = S::kThreads;
+  constexpr int KT = S::kKT;
   extern __shared__ __align__(128) unsigned char smem[];
   float2 *ts = reinterpret_cast<float2 *>(smem);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + T_STAGES * T_CHUNK_BYTES);
   float2 *xs = reinterpret_cast<float2 *>(smem + T_SMEM_FIXED);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o = lane & (LO - 1);   // output column of this lane
+  const int h = lane / LO;         // client half of this lane (0 when LO == 32)
+  const int cbase = warp * S::kWarpClients + h * T_RC;  // first of this thread's 8 clients in the group
 
   // which class / client group / output tile is this CTA?
   int ci = 0;
@@ -438,13 +470,20 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   const int local = (int)blockIdx.x - K.cta_begin;
   const int grp = local / K.tiles;
   const int tile = local - grp * K.tiles;
-  const int k0 = tile * T_KT;
+  const int k0 = tile * KT;
   const int D = K.D, Dp = K.Dp, L = K.L;
   const int n_out = K.n_out;
   const int nchunks = (L + T_JC - 1) / T_JC;
 
+  // bars[0..S): "stage is full" (TMA transaction count); bars[S..2S): "stage is free"
+  // (one arrival per warp).  The warps of a CTA never wait for each other inside the
+  // tap loop: a warp releases a stage and moves on; the producer thread refills the
+  // stage of the PREVIOUS chunk, which every warp has normally left long ago.
   if (tid == 0) {
-    for (int s = 0; s < T_STAGES; s++) mbar_init(&bars[s], 1);
+    for (int s = 0; s < T_STAGES; s++) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&bars[T_STAGES + s], S::kWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -464,8 +503,8 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   {
     const long long w0 = K.first + (long long)k0 * D;
     int row = tid / Dp, col = tid - row * Dp;
-    const int drow = T_THREADS / Dp, dcol = T_THREADS - drow * Dp;
-    for (int e = tid; e < K.xs_len; e += T_THREADS) {
+    const int drow = NT / Dp, dcol = NT - drow * Dp;
+    for (int e = tid; e < K.xs_len; e += NT) {
       if (col < D) {
         const long long ab = w0 + (long long)row * D + col;
         cp_async_8(xs + e, ring + ((unsigned)((unsigned long long)ab) & mask));
@@ -482,15 +521,9 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
-  // per-thread output rows of the 8 clients of this warp (-1 = padding slot); loaded
-  // now so the epilogue does not start with a chain of dependent global loads
-  int off[T_RC];
-  {
-    const int *mo = member_off + K.members_off + grp * T_CG + warp * T_RC;
-#pragma unroll
-    for (int c = 0; c < T_RC; c++) off[c] = __ldg(mo + c);
-  }
-  const bool warp_active = off[0] >= 0;  // members are packed from the front of a group
+  // members are packed from the front of a group: a warp whose first client is a
+  // padding slot has nothing to compute (it still takes part in the barriers)
+  const bool warp_active = grp * T_CG + warp * S::kWarpClients < K.n_members;
 
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -501,18 +534,19 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
 #pragma unroll
     for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
 
-  const float2 *xb0 = xs + lane * Dp;
-  const float2 *xb1 = xb0 + 32 * Dp;
-  const float2 *xb2 = xb1 + 32 * Dp;
-  const float2 *xb3 = xb2 + 32 * Dp;
+  const float2 *xb0 = xs + o * Dp;
+  const float2 *xb1 = xb0 + LO * Dp;
+  const float2 *xb2 = xb1 + LO * Dp;
+  const float2 *xb3 = xb2 + LO * Dp;
 
   for (int ch = 0; ch < nchunks; ch++) {
     const int s = ch % T_STAGES;
     mbar_wait(&bars[s], (unsigned)((ch / T_STAGES) & 1));
     if (warp_active) {
       const int len = min(T_JC, L - ch * T_JC);
-      const float4 *tp = reinterpret_cast<const float4 *>(ts + s * T_CHUNK_F2 + warp * T_RC);
+      const float4 *tp = reinterpret_cast<const float4 *>(ts + s * T_CHUNK_F2 + cbase);
       const int fbase = ch * T_JC;
+#ifdef XL_TILE_EXPLICIT_PREFETCH
       // operands are fetched one tap ahead of the FMAs that consume them (the
       // fetch past the end of a chunk reads valid shared memory and is discarded)
       float2 xn[T_RK];
@@ -523,12 +557,14 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       xn[3] = xb3[fbase];
 #pragma unroll
       for (int q = 0; q < T_RC / 2; q++) tn[q] = tp[q];
+#endif
 #pragma unroll 1
-      for (int f = 0; f < len; f += 8) {
+      for (int f = 0; f < len; f += T_UNROLL) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < T_UNROLL; u++) {
           float2 x[T_RK];
           float4 tq[T_RC / 2];
+#ifdef XL_TILE_EXPLICIT_PREFETCH
 #pragma unroll
           for (int i = 0; i < T_RK; i++) x[i] = xn[i];
 #pragma unroll
@@ -540,6 +576,14 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
           xn[3] = xb3[fbase + fn];
 #pragma unroll
           for (int q = 0; q < T_RC / 2; q++) tn[q] = tp[fn * (T_CG / 2) + q];
+#else
+          x[0] = xb0[fbase + f + u];
+          x[1] = xb1[fbase + f + u];
+          x[2] = xb2[fbase + f + u];
+          x[3] = xb3[fbase + f + u];
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#endif
 #pragma unroll
           for (int i = 0; i < T_RK; i++) {
 #pragma unroll
@@ -558,236 +602,55 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
         }
       }
     }
-    __syncthreads();  // every warp is done with stage s
-    if (tid == 0 && ch + T_STAGES < nchunks) {
-      const int nx = ch + T_STAGES;
-      const unsigned bytes = (unsigned)min(T_JC, L - nx * T_JC) * T_CG * 8u;
-      mbar_expect_tx(&bars[s], bytes);
-      tma_bulk_g2s(ts + s * T_CHUNK_F2, gt + (long long)nx * T_CHUNK_F2, bytes, &bars[s]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[T_STAGES + s]);  // this warp is done with stage s
+    if (tid == 0 && ch >= 1) {
+      const int pc = ch - 1, nx = pc + T_STAGES;
+      if (nx < nchunks) {
+        const int ps = pc % T_STAGES;
+        mbar_wait(&bars[T_STAGES + ps], (unsigned)((pc / T_STAGES) & 1));  // all warps left chunk pc
+        const unsigned bytes = (unsigned)min(T_JC, L - nx * T_JC) * T_CG * 8u;
+        mbar_expect_tx(&bars[ps], bytes);
+        tma_bulk_g2s(ts + ps * T_CHUNK_F2, gt + (long long)nx * T_CHUNK_F2, bytes, &bars[ps]);
+      }
     }
   }
 
   // epilogue: derotate with the pre-computed oscillator and store (coalesced in k).
   // The oscillator table is [k][32 clients]: this thread's 8 clients are 64
-  // contiguous bytes per output.  All loads are issued before their first use.
+  // contiguous bytes per output.  The loads of two outputs (and the clients' output
+  // row offsets) are in flight together before the first use.
   if (warp_active) {
-    const float4 *pt = reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride + warp * T_RC);
+    int off[T_RC];
+    {
+      const int *mo = member_off + K.members_off + grp * T_CG + cbase;
 #pragma unroll
-    for (int i = 0; i < T_RK; i++) {
-      const int k = k0 + lane + 32 * i;
-      if (k >= n_out) continue;
-      float4 ph[T_RC / 2];
-#pragma unroll
-      for (int q = 0; q < T_RC / 2; q++) ph[q] = __ldg(pt + (size_t)k * 16 + q);
-#pragma unroll
-      for (int q = 0; q < T_RC / 2; q++) {
-        if (off[2 * q] >= 0)
-          out[off[2 * q] + k] = cmul_unfused(acc[i][2 * q], make_float2(ph[q].x, ph[q].y));  // src/xlating.c:70
-        if (off[2 * q + 1] >= 0)
-          out[off[2 * q + 1] + k] = cmul_unfused(acc[i][2 * q + 1], make_float2(ph[q].z, ph[q].w));
-      }
+      for (int c = 0; c < T_RC; c++) off[c] = __ldg(mo + c);  // -1 = padding slot
     }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// tiled multi-client FIR, packed-FMA version (fma.rn.f32x2 -> SASS FFMA2)
-//
-// The FP32 pipe retires 128 FMA/clk/SM either as 4 scalar FFMA or as 2 packed FFMA2
-// per scheduler and clock; packed math halves the issue slots the FMAs need, which
-// leaves room for the shared-memory loads (and for co-resident kernels such as the
-// oscillator pre-pass) without starving the pipe.  To use packed operands with no
-// per-tap shuffling the complex MAC is split into two real-scaled sums,
-//     A1 += (xr, xi) * (tr, tr)        A2 += (xr, xi) * (ti, ti)
-//     re = A1.x - A2.y                 im = A1.y + A2.x          (once, at the end)
-// so x comes straight out of a 64-bit shared load and the taps are stored in
-// shared memory as (tr, tr, ti, ti): one 128-bit load yields both packed operands.
-//
-// CTA = 4 warps = 32 clients x 64 outputs.  In a warp, lane = (h, o): o = lane&15
-// selects the output column, h = lane>>4 the client half; thread tile 4 outputs
-// (o + 16 i) x 4 clients (4h + q).  The two half-warps read the same x (broadcast)
-// and two different 16-byte tap segments, so every shared load is ONE wavefront.
-// ---------------------------------------------------------------------------
-constexpr int U_THREADS = 128;
-constexpr int U_WARPS = 4;
-constexpr int U_RK = 4;
-constexpr int U_RC = 4;
-constexpr int U_KT = 16 * U_RK;          // 64 outputs per CTA
-constexpr int U_CG = U_WARPS * 2 * U_RC; // 32 clients per CTA
-constexpr int U_JC = 16;                 // flat taps per TMA chunk
-constexpr int U_STAGES = 3;
-constexpr int U_CHUNK_BYTES = U_JC * U_CG * 16;  // 8 KiB: (tr,tr,ti,ti) per client-tap
-constexpr int U_SMEM_FIXED = U_STAGES * U_CHUNK_BYTES + 64;
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ float2 unpack2(u64 v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-
-__global__ void __launch_bounds__(U_THREADS, 4)
-fir_tile2_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
-                      const float4 *__restrict__ tile_taps, const int *__restrict__ member_off,
-                      const float2 *__restrict__ phases, float2 *__restrict__ out) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  ulonglong2 *ts = reinterpret_cast<ulonglong2 *>(smem);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + U_STAGES * U_CHUNK_BYTES);
-  float2 *xs = reinterpret_cast<float2 *>(smem + U_SMEM_FIXED);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int o = lane & 15, h = lane >> 4;
-
-  int ci = 0;
-  while (ci + 1 < P.n_classes && (int)blockIdx.x >= P.cls[ci + 1].cta_begin) ci++;
-  const TileClass &K = P.cls[ci];
-  const int local = (int)blockIdx.x - K.cta_begin;
-  const int grp = local / K.tiles;
-  const int tile = local - grp * K.tiles;
-  const int k0 = tile * U_KT;
-  const int D = K.D, Dp = K.Dp, L = K.L;
-  const int n_out = K.n_out;
-  const int nchunks = (L + U_JC - 1) / U_JC;
-
-  if (tid == 0) {
-    for (int s = 0; s < U_STAGES; s++) mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  // taps of this client group: [flat tap][32 clients] x 16 B
-  const float4 *gt = tile_taps + K.taps_off + (long long)grp * L * U_CG;
-  if (tid == 0) {
-    for (int s = 0; s < U_STAGES && s < nchunks; s++) {
-      const unsigned bytes = (unsigned)min(U_JC, L - s * U_JC) * U_CG * 16u;
-      mbar_expect_tx(&bars[s], bytes);
-      tma_bulk_g2s(ts + s * (U_JC * U_CG), gt + (long long)s * (U_JC * U_CG), bytes, &bars[s]);
-    }
-  }
-
-  // input tile, skewed layout (see TileClass): coalesced 8-byte cp.async
-  {
-    const long long w0 = K.first + (long long)k0 * D;
-    int row = tid / Dp, col = tid - row * Dp;
-    const int drow = U_THREADS / Dp, dcol = U_THREADS - drow * Dp;
-    for (int e = tid; e < K.xs_len; e += U_THREADS) {
-      if (col < D) {
-        const long long ab = w0 + (long long)row * D + col;
-        cp_async_8(xs + e, ring + ((unsigned)((unsigned long long)ab) & mask));
-      } else {
-        xs[e] = make_float2(0.f, 0.f);
+    const float4 *pt =
+        reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride + cbase);
+#pragma unroll
+    for (int i2 = 0; i2 < T_RK; i2 += 2) {
+      float4 ph[2][T_RC / 2];
+#pragma unroll
+      for (int ii = 0; ii < 2; ii++) {
+        const int k = min(k0 + o + LO * (i2 + ii), n_out - 1);  // clamped: always a valid row
+#pragma unroll
+        for (int q = 0; q < T_RC / 2; q++) ph[ii][q] = __ldg(pt + (size_t)k * 16 + q);
       }
-      row += drow;
-      col += dcol;
-      if (col >= Dp) {
-        col -= Dp;
-        row++;
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-
-  int off[U_RC];
-  {
-    const int *mo = member_off + K.members_off + grp * U_CG + warp * (2 * U_RC) + h * U_RC;
 #pragma unroll
-    for (int q = 0; q < U_RC; q++) off[q] = __ldg(mo + q);
-  }
-  // members are packed from the front of a group: a warp whose first client is a
-  // padding slot has nothing to do
-  const bool warp_active = __shfl_sync(0xffffffffu, off[0], 0) >= 0;
-
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  u64 A1[U_RK][U_RC], A2[U_RK][U_RC];
+      for (int ii = 0; ii < 2; ii++) {
+        const int i = i2 + ii;
+        const int k = k0 + o + LO * i;
+        if (k >= n_out) continue;
 #pragma unroll
-  for (int i = 0; i < U_RK; i++)
-#pragma unroll
-    for (int q = 0; q < U_RC; q++) A1[i][q] = A2[i][q] = 0ull;
-
-  const u64 *xq = reinterpret_cast<const u64 *>(xs);
-  const u64 *xb0 = xq + o * Dp;
-  const u64 *xb1 = xb0 + 16 * Dp;
-  const u64 *xb2 = xb1 + 16 * Dp;
-  const u64 *xb3 = xb2 + 16 * Dp;
-
-  for (int ch = 0; ch < nchunks; ch++) {
-    const int s = ch % U_STAGES;
-    mbar_wait(&bars[s], (unsigned)((ch / U_STAGES) & 1));
-    if (warp_active) {
-      const int len = min(U_JC, L - ch * U_JC);
-      const ulonglong2 *tp = ts + s * (U_JC * U_CG) + warp * (2 * U_RC) + h * U_RC;
-      const int fbase = ch * U_JC;
-      u64 xn[U_RK];
-      ulonglong2 tn[U_RC];
-      xn[0] = xb0[fbase];
-      xn[1] = xb1[fbase];
-      xn[2] = xb2[fbase];
-      xn[3] = xb3[fbase];
-#pragma unroll
-      for (int q = 0; q < U_RC; q++) tn[q] = tp[q];
-#pragma unroll 1
-      for (int f = 0; f < len; f += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          u64 x[U_RK];
-          ulonglong2 t[U_RC];
-#pragma unroll
-          for (int i = 0; i < U_RK; i++) x[i] = xn[i];
-#pragma unroll
-          for (int q = 0; q < U_RC; q++) t[q] = tn[q];
-          const int fn = f + u + 1;  // one tap ahead; the read past a chunk is discarded
-          xn[0] = xb0[fbase + fn];
-          xn[1] = xb1[fbase + fn];
-          xn[2] = xb2[fbase + fn];
-          xn[3] = xb3[fbase + fn];
-#pragma unroll
-          for (int q = 0; q < U_RC; q++) tn[q] = tp[fn * U_CG + q];
-#pragma unroll
-          for (int i = 0; i < U_RK; i++) {
-#pragma unroll
-            for (int q = 0; q < U_RC; q++) {
-              A1[i][q] = ffma2(x[i], t[q].x, A1[i][q]);
-              A2[i][q] = ffma2(x[i], t[q].y, A2[i][q]);
-            }
-          }
+        for (int q = 0; q < T_RC / 2; q++) {
+          if (off[2 * q] >= 0)
+            out[off[2 * q] + k] =
+                cmul_unfused(acc[i][2 * q], make_float2(ph[ii][q].x, ph[ii][q].y));  // src/xlating.c:70
+          if (off[2 * q + 1] >= 0)
+            out[off[2 * q + 1] + k] = cmul_unfused(acc[i][2 * q + 1], make_float2(ph[ii][q].z, ph[ii][q].w));
         }
-      }
-    }
-    __syncthreads();
-    if (tid == 0 && ch + U_STAGES < nchunks) {
-      const int nx = ch + U_STAGES;
-      const unsigned bytes = (unsigned)min(U_JC, L - nx * U_JC) * U_CG * 16u;
-      mbar_expect_tx(&bars[s], bytes);
-      tma_bulk_g2s(ts + s * (U_JC * U_CG), gt + (long long)nx * (U_JC * U_CG), bytes, &bars[s]);
-    }
-  }
-
-  if (warp_active) {
-    const float4 *pt = reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride +
-                                                        warp * (2 * U_RC) + h * U_RC);
-#pragma unroll
-    for (int i = 0; i < U_RK; i++) {
-      const int k = k0 + o + 16 * i;
-      if (k >= n_out) continue;
-      float4 ph[U_RC / 2];
-#pragma unroll
-      for (int q = 0; q < U_RC / 2; q++) ph[q] = __ldg(pt + (size_t)k * 16 + q);
-#pragma unroll
-      for (int q = 0; q < U_RC; q++) {
-        if (off[q] < 0) continue;
-        const float2 a1 = unpack2(A1[i][q]), a2 = unpack2(A2[i][q]);
-        const float2 acc = make_float2(a1.x - a2.y, a1.y + a2.x);
-        const float2 pq = (q & 1) ? make_float2(ph[q / 2].z, ph[q / 2].w) : make_float2(ph[q / 2].x, ph[q / 2].y);
-        out[off[q] + k] = cmul_unfused(acc, pq);  // src/xlating.c:70
       }
     }
   }
