@@ -52,14 +52,21 @@ enum { XLG_FMT_CU8 = 0, XLG_FMT_CS8 = 1, XLG_FMT_CS16 = 2 };
 #define XLG_INPUT_DEVICE 0x100u /* `input` is a device pointer on the group's GPU (already staged) */
 #define XLG_PATH_Q15 0x200u     /* Q15 integer path (src/xlating.c:92-140) instead of cf32 */
 
-/* number of blocks that may be in flight; outputs of ticket t stay valid until
- * ticket t + XLG_SLOTS is submitted */
+/* depth of the device pipeline (blocks in flight).  Outputs of ticket t stay valid
+ * until ticket t + XLG_SLOTS (or t + host_ring, see xlg_create_ex) is submitted;
+ * after that xlg_wait / xlg_output return -ESTALE. */
 #define XLG_SLOTS 4
 
 /* One wideband stream on CUDA device `device`.  max_input_len is the largest
  * block, in scalar elements (like create_frequency_xlating_filter's
  * max_input_buffer_length, src/xlating.c:553). */
 int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input_len, uint32_t flags, xlg_group **out);
+/* Same, with `host_ring` >= XLG_SLOTS result entries kept in pinned host memory: the
+ * outputs of ticket t stay readable until ticket t + host_ring is submitted, so a
+ * consumer blocked on a slow socket has the slack the reference gets from its
+ * per-client queue of queue_size blocks (src/config.c:183, src/queue.c:42-85). */
+int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_input_len, uint32_t flags, uint32_t host_ring,
+                  xlg_group **out);
 void xlg_destroy(xlg_group *g);
 
 /* Attach / detach a client.  Arguments as create_frequency_xlating_filter

@@ -46,7 +46,7 @@ REFERENCE_SYMBOLS = (
     + [f"process_{v}_{f}_{o}" for v in ("native", "optimized") for f in ("cu8", "cs8", "cs16") for o in ("cf32", "cs16")]
 )
 GROUP_SYMBOLS = [
-    "xlg_create", "xlg_destroy", "xlg_add_client", "xlg_remove_client", "xlg_client_count", "xlg_submit",
+    "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_remove_client", "xlg_client_count", "xlg_submit",
     "xlg_wait", "xlg_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
     "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info",
 ]
@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
                 fn.restype = None
     L.xlg_create.argtypes = [C.c_int, u32, u32, u32, C.POINTER(vp)]
     L.xlg_create.restype = C.c_int
+    L.xlg_create_ex.argtypes = [C.c_int, u32, u32, u32, u32, C.POINTER(vp)]
+    L.xlg_create_ex.restype = C.c_int
     L.xlg_destroy.argtypes = [vp]
     L.xlg_destroy.restype = None
     L.xlg_add_client.argtypes = [vp, u32, C.POINTER(C.c_float), sz, i32, C.POINTER(C.c_int)]
@@ -204,10 +206,13 @@ class XlatingFilter:
 class Group:
     """Many clients on one wideband stream (include/xlating_group.h)."""
 
-    def __init__(self, sampling_freq: int, max_input_len: int, device: int = 0, flags: int = 0):
+    def __init__(self, sampling_freq: int, max_input_len: int, device: int = 0, flags: int = 0, host_ring: int = 0):
         self._L = lib()
         h = C.c_void_p()
-        code = self._L.xlg_create(device, sampling_freq, max_input_len, flags, C.byref(h))
+        if host_ring:
+            code = self._L.xlg_create_ex(device, sampling_freq, max_input_len, flags, host_ring, C.byref(h))
+        else:
+            code = self._L.xlg_create(device, sampling_freq, max_input_len, flags, C.byref(h))
         self._h = None
         if code != 0:
             raise RuntimeError(f"xlg_create -> {code} (no CPU fallback)")
@@ -362,3 +367,65 @@ def client_plan(fs: int, rates, tw=None):
         plan.append({"rate": rate, "decimation": fs // rate, "center": center,
                      "cutoff": rate // 2, "tw": tw if tw is not None else rate // 5})
     return plan
+
+
+# ---------------------------------------------------------------------------
+# host-side server model in C (sdr-server_b200/host): ticket queue, dsp_worker,
+# stream (sdr_callback fan-out).  Bound here only for the tests.
+# ---------------------------------------------------------------------------
+HOST_LIB_PATH = os.path.join(HERE, "lib", "libxlating_host.so")
+
+
+class XlClientConfig(C.Structure):
+    _fields_ = [("center_freq", C.c_uint32), ("sampling_rate", C.c_uint32), ("band_freq", C.c_uint32),
+                ("destination", C.c_uint8), ("client_socket", C.c_int), ("id", C.c_uint32)]
+
+
+class XlStreamConfig(C.Structure):
+    _fields_ = [("sdr_type", C.c_int), ("band_sampling_rate", C.c_uint32), ("buffer_size", C.c_uint32),
+                ("queue_size", C.c_int), ("lpf_cutoff_rate", C.c_int), ("base_path", C.c_char_p),
+                ("device", C.c_int)]
+
+
+_host = None
+
+
+def host_lib() -> C.CDLL:
+    global _host
+    if _host is not None:
+        return _host
+    if not os.path.exists(HOST_LIB_PATH):
+        raise RuntimeError(f"{HOST_LIB_PATH} is missing: run `make -C {HERE}/host`")
+    lib()  # libxlating_b200.so first (rpath $ORIGIN also finds it)
+    H = C.CDLL(HOST_LIB_PATH)
+    vp = C.c_void_p
+    H.xl_tq_create.argtypes = [C.c_int, C.POINTER(vp)]
+    H.xl_tq_create.restype = C.c_int
+    H.xl_tq_put.argtypes = [vp, C.c_int64]
+    H.xl_tq_put.restype = None
+    H.xl_tq_take.argtypes = [vp]
+    H.xl_tq_take.restype = C.c_int64
+    H.xl_tq_complete.argtypes = [vp]
+    H.xl_tq_complete.restype = None
+    H.xl_tq_interrupt.argtypes = [vp]
+    H.xl_tq_interrupt.restype = None
+    H.xl_tq_destroy.argtypes = [vp]
+    H.xl_tq_destroy.restype = None
+    H.xl_tq_overruns.argtypes = [vp]
+    H.xl_tq_overruns.restype = C.c_uint64
+    H.xl_stream_create.argtypes = [C.POINTER(XlStreamConfig), C.POINTER(vp)]
+    H.xl_stream_create.restype = C.c_int
+    H.xl_stream_add_client.argtypes = [vp, C.POINTER(XlClientConfig)]
+    H.xl_stream_add_client.restype = C.c_int
+    H.xl_stream_remove_client.argtypes = [vp, C.c_uint32]
+    H.xl_stream_remove_client.restype = C.c_int
+    H.xl_stream_push.argtypes = [vp, vp, C.c_uint32]
+    H.xl_stream_push.restype = C.c_int
+    H.xl_stream_flush.argtypes = [vp]
+    H.xl_stream_flush.restype = None
+    H.xl_stream_destroy.argtypes = [vp]
+    H.xl_stream_destroy.restype = None
+    H.xl_stream_client_count.argtypes = [vp]
+    H.xl_stream_client_count.restype = C.c_int
+    _host = H
+    return H

@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -82,8 +83,8 @@ struct HostClient {
 
 struct Slot {
   void *d_raw = nullptr, *h_raw = nullptr;
-  float2 *d_out = nullptr, *h_out = nullptr;
-  short2 *d_qout = nullptr, *h_qout = nullptr;
+  float2 *d_out = nullptr;
+  short2 *d_qout = nullptr;
   float2 *d_phases = nullptr;
   short2 *d_qphases = nullptr;
   BlkInfo *d_blk = nullptr;
@@ -91,11 +92,9 @@ struct Slot {
   cudaEvent_t ev_h2d = nullptr, ev_conv = nullptr, ev_phase = nullptr, ev_fir = nullptr, ev_done = nullptr;
   cudaEvent_t pf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool pf_conv = false, pf_phase = false, pf_tile = false, pf_gen = false;
-  int64_t ticket = -1;
+  std::atomic<int64_t> ticket{-1};
   bool q15 = false;
   bool harvested = true;
-  std::vector<int> n_out;    // per client id
-  std::vector<int> out_off;  // per client id
   uint64_t tile_macs = 0, algo_macs = 0, out_samples = 0, in_samples = 0;
 };
 
@@ -134,6 +133,19 @@ static bool drv(const char *name, F *fn) {
   *fn = reinterpret_cast<F>(p);
   return true;
 }
+
+// Host-visible results of one ticket.  There are `host_ring` of these (>= XLG_SLOTS):
+// the device pipeline is XLG_SLOTS deep, but results stay readable for host_ring
+// tickets so that a consumer thread blocked on a slow socket does not lose data
+// (the reference absorbs that with a 64-block queue per client, src/config.c:183).
+struct HostOut {
+  std::atomic<int64_t> ticket{-1};
+  bool q15 = false;
+  float2 *h_out = nullptr;   // pinned; nullptr for XLG_OUT_DEVICE groups
+  short2 *h_qout = nullptr;
+  std::vector<int> n_out;    // per client id
+  std::vector<int> out_off;  // per client id
+};
 
 struct TileClassHost {
   TileClass k;
@@ -177,7 +189,9 @@ struct xlg_group {
   bool dirty = true;
 
   Slot slots[XLG_SLOTS];
-  int64_t next_ticket = 0;
+  std::vector<HostOut> ring_out;  // indexed by ticket % ring_out.size()
+  std::vector<void *> retired_host;
+  std::atomic<int64_t> next_ticket{0};
   cudaEvent_t ev_last_conv = nullptr;
   cudaEvent_t ev_last_conv_ref = nullptr;  // ev_conv of the previous block's slot (history dependency)
   bool have_last_conv = false;
@@ -204,15 +218,13 @@ static void slot_free(Slot &s) {
   if (s.d_raw) cudaFree(s.d_raw);
   if (s.h_raw) cudaFreeHost(s.h_raw);
   if (s.d_out) cudaFree(s.d_out);
-  if (s.h_out) cudaFreeHost(s.h_out);
   if (s.d_qout) cudaFree(s.d_qout);
-  if (s.h_qout) cudaFreeHost(s.h_qout);
   if (s.d_phases) cudaFree(s.d_phases);
   if (s.d_qphases) cudaFree(s.d_qphases);
   if (s.d_blk) cudaFree(s.d_blk);
   s.d_raw = s.h_raw = nullptr;
-  s.d_out = s.h_out = nullptr;
-  s.d_qout = s.h_qout = nullptr;
+  s.d_out = nullptr;
+  s.d_qout = nullptr;
   s.d_phases = nullptr;
   s.d_qphases = nullptr;
   s.d_blk = nullptr;
@@ -311,29 +323,41 @@ static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
     const size_t cap = std::max<size_t>(need + need / 4, 1024);
     for (Slot &s : g->slots) {
       if (s.d_out) cudaFree(s.d_out);
-      if (s.h_out) cudaFreeHost(s.h_out);
-      s.d_out = s.h_out = nullptr;
+      s.d_out = nullptr;
       CU_OK(cudaMalloc(&s.d_out, cap * sizeof(float2)));
-      if (!dev_out) CU_OK(cudaHostAlloc(&s.h_out, cap * sizeof(float2), cudaHostAllocDefault));
       if (g->q_alloc) {
         if (s.d_qout) cudaFree(s.d_qout);
-        if (s.h_qout) cudaFreeHost(s.h_qout);
         if (s.d_qphases) cudaFree(s.d_qphases);
-        s.d_qout = s.h_qout = nullptr;
+        s.d_qout = nullptr;
         s.d_qphases = nullptr;
         CU_OK(cudaMalloc(&s.d_qout, cap * sizeof(short2)));
         CU_OK(cudaMalloc(&s.d_qphases, cap * sizeof(short2)));
-        if (!dev_out) CU_OK(cudaHostAlloc(&s.h_qout, cap * sizeof(short2), cudaHostAllocDefault));
+      }
+    }
+    for (HostOut &h : g->ring_out) {
+      std::lock_guard<std::mutex> lk(g->mu);
+      h.ticket.store(-1);  // resized: older results are gone
+      // a consumer thread may still be writing an old result to its socket: the old
+      // pinned arenas are retired, not freed, until the group is destroyed
+      if (h.h_out) g->retired_host.push_back(h.h_out);
+      if (h.h_qout) g->retired_host.push_back(h.h_qout);
+      h.h_out = nullptr;
+      h.h_qout = nullptr;
+      if (!dev_out) {
+        CU_OK(cudaHostAlloc(&h.h_out, cap * sizeof(float2), cudaHostAllocDefault));
+        if (g->q_alloc) CU_OK(cudaHostAlloc(&h.h_qout, cap * sizeof(short2), cudaHostAllocDefault));
       }
     }
     g->arena_cap = cap;
   }
   if (need_q && !g->q_alloc) {
     for (Slot &s : g->slots) {
-      CU_OK(cudaMalloc(&s.d_qout, g->arena_cap * sizeof(short2)));
-      CU_OK(cudaMalloc(&s.d_qphases, g->arena_cap * sizeof(short2)));
-      if (!dev_out) CU_OK(cudaHostAlloc(&s.h_qout, g->arena_cap * sizeof(short2), cudaHostAllocDefault));
+      CU_OK(cudaMalloc(&s.d_qout, std::max<size_t>(g->arena_cap, 1) * sizeof(short2)));
+      CU_OK(cudaMalloc(&s.d_qphases, std::max<size_t>(g->arena_cap, 1) * sizeof(short2)));
     }
+    if (!dev_out)
+      for (HostOut &h : g->ring_out)
+        CU_OK(cudaHostAlloc(&h.h_qout, std::max<size_t>(g->arena_cap, 1) * sizeof(short2), cudaHostAllocDefault));
     g->q_alloc = true;
   }
   return 0;
@@ -629,7 +653,14 @@ static void partition_create(xlg_group *g, int device) {
 // ---------------------------------------------------------------------------
 extern "C" int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input_len, uint32_t flags,
                           xlg_group **out) {
+  return xlg_create_ex(device, sampling_freq, max_input_len, flags, XLG_SLOTS, out);
+}
+
+extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_input_len, uint32_t flags,
+                             uint32_t host_ring, xlg_group **out) {
   if (out == nullptr || max_input_len < 2 || sampling_freq == 0) return -EINVAL;
+  if (host_ring < XLG_SLOTS) host_ring = XLG_SLOTS;
+  if (host_ring > 1024) return -EINVAL;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -655,6 +686,7 @@ extern "C" int xlg_create(int device, uint32_t sampling_freq, uint32_t max_input
   g->fs = sampling_freq;
   g->max_input_len = max_input_len;
   g->flags = flags;
+  g->ring_out = std::vector<HostOut>(host_ring);
   int rc = 0;
   auto fail = [&](int code) {
     xlg_destroy(g);
@@ -721,6 +753,11 @@ extern "C" void xlg_destroy(xlg_group *g) {
     for (int i = 0; i < 8; i++)
       if (s.pf[i]) cudaEventDestroy(s.pf[i]);
   }
+  for (HostOut &h : g->ring_out) {
+    if (h.h_out) cudaFreeHost(h.h_out);
+    if (h.h_qout) cudaFreeHost(h.h_qout);
+  }
+  for (void *p : g->retired_host) cudaFreeHost(p);
   if (g->ev_last_conv) cudaEventDestroy(g->ev_last_conv);
   if (g->ev_t0) cudaEventDestroy(g->ev_t0);
   if (g->ev_t1) cudaEventDestroy(g->ev_t1);
@@ -856,10 +893,11 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     if (rc) return rc;
   }
 
-  const int64_t ticket = g->next_ticket;
+  const int64_t ticket = g->next_ticket.load();
   Slot &s = g->slots[ticket % XLG_SLOTS];
+  HostOut &ho = g->ring_out[ticket % (int64_t)g->ring_out.size()];
   const auto t_enter = std::chrono::steady_clock::now();
-  if (s.ticket >= 0) {
+  if (s.ticket.load() >= 0) {
     CU_OK(cudaEventSynchronize(s.ev_done));
     g->host_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                            std::chrono::steady_clock::now() - t_enter).count();
@@ -873,8 +911,14 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
 
   // host mirror of the per-client output counts (same integer formula as the
   // oscillator pre-pass kernel)
-  s.n_out.assign(g->clients.size(), 0);
-  s.out_off.assign(g->clients.size(), 0);
+  {
+    // consumers read this entry's metadata under the same mutex (xlg_output)
+    std::lock_guard<std::mutex> lk(g->mu);
+    ho.ticket.store(-1);  // the entry is being recycled
+    ho.n_out.assign(g->clients.size(), 0);
+    ho.out_off.assign(g->clients.size(), 0);
+    ho.q15 = q15;
+  }
   s.q15 = q15;
   s.tile_macs = s.algo_macs = s.out_samples = 0;
   s.in_samples = (uint64_t)n;
@@ -887,8 +931,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     int n_out = 0;
     if (last_ok >= first) n_out = (int)((last_ok - first) / (long long)h.D) + 1;
     if (n_out > h.out_cap) n_out = h.out_cap;
-    s.n_out[i] = n_out;
-    s.out_off[i] = h.out_off;
+    ho.n_out[i] = n_out;
+    ho.out_off[i] = h.out_off;
     h.hist = (S + n) - (first + (long long)n_out * (long long)h.D);
     s.out_samples += (uint64_t)n_out;
     s.algo_macs += (uint64_t)n_out * h.T;
@@ -969,7 +1013,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     size_t smem = 0;
     for (TileClassHost &ch : g->classes) {
       const HostClient &h0 = g->clients[ch.members[0]];
-      const int n_out = s.n_out[ch.members[0]];
+      const int n_out = ho.n_out[ch.members[0]];
       if (n_out <= 0) continue;
       TileClass k = ch.k;
       // hist was already advanced above; recover this block's window start
@@ -1018,13 +1062,13 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   if (!dev_out && g->arena_cap > 0 && nc > 0) {
     size_t used = 0;
     for (size_t i = 0; i < g->clients.size(); i++)
-      if (g->clients[i].active) used = std::max(used, (size_t)g->clients[i].out_off + (size_t)s.n_out[i]);
+      if (g->clients[i].active) used = std::max(used, (size_t)g->clients[i].out_off + (size_t)ho.n_out[i]);
     CU_OK(cudaStreamWaitEvent(g->s_out, s.ev_fir, 0));
     if (used > 0) {
       if (q15)
-        CU_OK(cudaMemcpyAsync(s.h_qout, s.d_qout, used * sizeof(short2), cudaMemcpyDeviceToHost, g->s_out));
+        CU_OK(cudaMemcpyAsync(ho.h_qout, s.d_qout, used * sizeof(short2), cudaMemcpyDeviceToHost, g->s_out));
       else
-        CU_OK(cudaMemcpyAsync(s.h_out, s.d_out, used * sizeof(float2), cudaMemcpyDeviceToHost, g->s_out));
+        CU_OK(cudaMemcpyAsync(ho.h_out, s.d_out, used * sizeof(float2), cudaMemcpyDeviceToHost, g->s_out));
     }
     CU_OK(cudaEventRecord(s.ev_done, g->s_out));
   } else {
@@ -1036,38 +1080,47 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     g->qS += n;
   else
     g->S += n;
-  s.ticket = ticket;
+  s.ticket.store(ticket);
+  ho.ticket.store(ticket);
   s.harvested = false;
-  g->next_ticket++;
+  g->next_ticket.store(ticket + 1);
   g->host_submit_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                            std::chrono::steady_clock::now() - t_enter).count();
   return ticket;
 }
 
 extern "C" int xlg_wait(xlg_group *g, int64_t ticket) {
-  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket) return -EINVAL;
-  if (ticket + XLG_SLOTS < g->next_ticket) return -ESTALE;
+  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket.load()) return -EINVAL;
+  HostOut &ho = g->ring_out[ticket % (int64_t)g->ring_out.size()];
+  if (ho.ticket.load() != ticket) return -ESTALE;  // overwritten: the consumer fell too far behind
   Slot &s = g->slots[ticket % XLG_SLOTS];
-  if (s.ticket != ticket) return -ESTALE;
-  cudaSetDevice(g->device);
-  CU_OK(cudaEventSynchronize(s.ev_done));
-  std::lock_guard<std::mutex> lk(g->mu);
-  harvest_locked(g, s);
-  return 0;
+  if (s.ticket.load() == ticket) {
+    cudaSetDevice(g->device);
+    CU_OK(cudaEventSynchronize(s.ev_done));
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (s.ticket.load() == ticket) harvest_locked(g, s);
+  }
+  // else: the device slot already serves a later ticket, which xlg_submit only allows
+  // after this ticket's copy-out completed
+  return ho.ticket.load() == ticket ? 0 : -ESTALE;
 }
 
 extern "C" int xlg_output(xlg_group *g, int64_t ticket, int client_id, const void **out, size_t *out_len) {
-  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket) return -EINVAL;
-  Slot &s = g->slots[ticket % XLG_SLOTS];
-  if (s.ticket != ticket) return -ESTALE;
-  if (client_id < 0 || client_id >= (int)s.n_out.size()) return -EINVAL;
+  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket.load()) return -EINVAL;
+  HostOut &ho = g->ring_out[ticket % (int64_t)g->ring_out.size()];
+  std::lock_guard<std::mutex> lk(g->mu);
+  if (ho.ticket.load() != ticket) return -ESTALE;
+  if (client_id < 0 || client_id >= (int)ho.n_out.size()) return -EINVAL;
   const bool dev_out = (g->flags & XLG_OUT_DEVICE) != 0;
-  if (out_len) *out_len = (size_t)s.n_out[client_id];
+  if (out_len) *out_len = (size_t)ho.n_out[client_id];
   if (out) {
-    if (s.q15)
-      *out = (dev_out ? s.d_qout : s.h_qout) + s.out_off[client_id];
-    else
-      *out = (dev_out ? s.d_out : s.h_out) + s.out_off[client_id];
+    if (dev_out) {
+      Slot &s = g->slots[ticket % XLG_SLOTS];
+      if (s.ticket.load() != ticket) return -ESTALE;  // device arenas live XLG_SLOTS tickets
+      *out = ho.q15 ? (const void *)(s.d_qout + ho.out_off[client_id]) : (const void *)(s.d_out + ho.out_off[client_id]);
+    } else {
+      *out = ho.q15 ? (const void *)(ho.h_qout + ho.out_off[client_id]) : (const void *)(ho.h_out + ho.out_off[client_id]);
+    }
   }
   return 0;
 }
@@ -1145,11 +1198,11 @@ extern "C" int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset) {
   *p = g->prof;
   p->host_submit_ms = (double)g->host_submit_ns * 1e-6;
   p->host_wait_ms = (double)g->host_wait_ns * 1e-6;
-  p->submits = (uint64_t)g->next_ticket - g->host_count_base;
+  p->submits = (uint64_t)g->next_ticket.load() - g->host_count_base;
   if (reset) {
     memset(&g->prof, 0, sizeof(g->prof));
     g->host_submit_ns = g->host_wait_ns = 0;
-    g->host_count_base = (uint64_t)g->next_ticket;
+    g->host_count_base = (uint64_t)g->next_ticket.load();
   }
   return 0;
 }
