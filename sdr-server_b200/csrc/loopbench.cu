@@ -258,6 +258,129 @@ __global__ void __launch_bounds__(128, 3) k_v3(float *out, int passes, long long
   if (tid == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// ---- variant 4: v1 math inside the real kernel's tap pipeline ----
+// Same register tile and loads as v1, but the taps are streamed from global memory
+// through the 3-stage TMA ring with full/empty mbarriers exactly as
+// fir_tile_cf32_kernel does (32-tap chunks of 8 KiB).  Isolates what the chunked
+// pipeline costs relative to the resident-data loop.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int SYNC>  // 0: mbarrier release (current kernel), 1: __syncthreads per chunk
+__global__ void __launch_bounds__(128, 3) k_v4(float *out, int passes, long long *cycles, const float2 *gtaps) {
+  constexpr int JC = 32, ST = 3, CH = JC * 32;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2 *ts = reinterpret_cast<float2 *>(smem);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + ST * CH * 8);
+  float2 *xs = reinterpret_cast<float2 *>(smem + ST * CH * 8 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = 512;
+  const int xs_len = 127 * DP + L + 8;
+  for (int i = tid; i < xs_len; i += 128) xs[i] = make_float2(0.01f * (i % 11), 0.02f * (i % 5));
+  if (tid == 0) {
+    for (int s = 0; s < ST; s++) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&bars[ST + s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  float2 acc[4][8];
+  for (int i = 0; i < 4; i++)
+    for (int c = 0; c < 8; c++) acc[i][c] = make_float2(0.f, 0.f);
+  const float2 *xb0 = xs + lane * DP, *xb1 = xb0 + 32 * DP, *xb2 = xb1 + 32 * DP, *xb3 = xb2 + 32 * DP;
+  const int nchunks_pass = L / JC;
+  const int total = passes * nchunks_pass;
+  const float2 *gt = gtaps + (size_t)(blockIdx.x % 8) * L * 32;
+  if (tid == 0)
+    for (int s = 0; s < ST; s++) {
+      mbar_expect_tx(&bars[s], CH * 8);
+      tma_bulk_g2s(ts + s * CH, gt + (size_t)(s % nchunks_pass) * CH, CH * 8, &bars[s]);
+    }
+  long long t0 = clock64();
+  for (int ch = 0; ch < total; ch++) {
+    const int s = ch % ST;
+    mbar_wait(&bars[s], (unsigned)((ch / ST) & 1));
+    const float4 *tp = reinterpret_cast<const float4 *>(ts + s * CH + warp * 8);
+    const int fbase = (ch % nchunks_pass) * JC;
+#pragma unroll 1
+    for (int f = 0; f < JC; f += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        float2 x[4];
+        x[0] = xb0[fbase + f + u];
+        x[1] = xb1[fbase + f + u];
+        x[2] = xb2[fbase + f + u];
+        x[3] = xb3[fbase + f + u];
+        float4 tq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) tq[q] = tp[(f + u) * 16 + q];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+            a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+            a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+            a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+            a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+            a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+            a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+            a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+            a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+          }
+      }
+    }
+    if (SYNC) {
+      __syncthreads();
+      if (tid == 0 && ch + ST < total) {
+        mbar_expect_tx(&bars[s], CH * 8);
+        tma_bulk_g2s(ts + s * CH, gt + (size_t)((ch + ST) % nchunks_pass) * CH, CH * 8, &bars[s]);
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[ST + s]);
+      if (tid == 0 && ch >= 1) {
+        const int pc = ch - 1, nx = pc + ST;
+        if (nx < total) {
+          const int ps = pc % ST;
+          mbar_wait(&bars[ST + ps], (unsigned)((pc / ST) & 1));
+          mbar_expect_tx(&bars[ps], CH * 8);
+          tma_bulk_g2s(ts + ps * CH, gt + (size_t)(nx % nchunks_pass) * CH, CH * 8, &bars[ps]);
+        }
+      }
+    }
+  }
+  long long t1 = clock64();
+  float sacc = 0;
+  for (int i = 0; i < 4; i++)
+    for (int c = 0; c < 8; c++) sacc += acc[i][c].x + acc[i][c].y;
+  out[blockIdx.x * 128 + tid] = sacc;
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 template <typename K>
 static void run(const char *name, K kernel, int per_sm, size_t smem, int passes, double fma_per_thread_pass,
                 float *d_out, long long *d_cyc, int sms) {
@@ -287,6 +410,35 @@ static void run(const char *name, K kernel, int per_sm, size_t smem, int passes,
          per_sm, per_sm * 4, total / (best * 1e-3) / 1e12, best);
 }
 
+template <typename K>
+static void run4(const char *name, K kernel, int per_sm, size_t smem, int passes, double fma_per_thread_pass,
+                 float *d_out, long long *d_cyc, int sms, const float2 *gt) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int blocks = per_sm * sms;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  kernel<<<blocks, 128, smem>>>(d_out, 2, d_cyc, gt);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    printf("{\"bench\": \"%s\", \"error\": \"%s\"}\n", name, cudaGetErrorString(err));
+    return;
+  }
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    kernel<<<blocks, 128, smem>>>(d_out, passes, d_cyc, gt);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  const double total = fma_per_thread_pass * passes * 128.0 * blocks;
+  printf("{\"bench\": \"%s\", \"ctas_per_sm\": %d, \"warps_per_sm\": %d, \"tfma_per_s\": %.3f, \"ms\": %.4f}\n", name,
+         per_sm, per_sm * 4, total / (best * 1e-3) / 1e12, best);
+}
+
 int main(int argc, char **argv) {
   int passes = argc > 1 ? atoi(argv[1]) : 1000;
   cudaDeviceProp prop;
@@ -300,7 +452,13 @@ int main(int argc, char **argv) {
   const size_t smem2 = (size_t)LFLAT * 32 * 16 + (63 * DP + LFLAT + 8) * 8;
   const size_t smem3 = (size_t)LFLAT * 32 * 16 + (127 * DP + LFLAT + 8) * 8;
   printf("{\"smem_v1\": %zu, \"smem_v2\": %zu, \"smem_v3\": %zu}\n", smem1, smem2, smem3);
+  float2 *d_gt;
+  cudaMalloc(&d_gt, sizeof(float2) * 8 * 512 * 32);
+  cudaMemset(d_gt, 0, sizeof(float2) * 8 * 512 * 32);
+  const size_t smem4 = 3 * 32 * 32 * 8 + 64 + (127 * DP + 512 + 8) * 8;
   for (int per_sm = 1; per_sm <= 3; per_sm++) {
+    run4("v4_v1math_tma_ring_mbarrier", k_v4<0>, per_sm, smem4, passes / 5, 512 * 128.0, d_out, d_cyc, sms, d_gt);
+    run4("v4_v1math_tma_ring_syncthreads", k_v4<1>, per_sm, smem4, passes / 5, 512 * 128.0, d_out, d_cyc, sms, d_gt);
     run("v1_ffma_4x8", k_v1<0>, per_sm, smem1, passes, LFLAT * 128.0, d_out, d_cyc, sms);
     run("v2_ffma2_4x4_plain", k_v2<0>, per_sm, smem2, passes, LFLAT * 64.0, d_out, d_cyc, sms);
     run("v2_ffma2_4x4_pingpong", k_v2<1>, per_sm, smem2, passes, LFLAT * 64.0, d_out, d_cyc, sms);

@@ -191,6 +191,8 @@ struct xlg_group {
   Slot slots[XLG_SLOTS];
   std::vector<HostOut> ring_out;  // indexed by ticket % ring_out.size()
   std::vector<void *> retired_host;
+  long long *d_trace = nullptr;  // XLATING_B200_TRACE=1: per-CTA timeline of the tiled kernel
+  int trace_ctas = 0;
   std::atomic<int64_t> next_ticket{0};
   cudaEvent_t ev_last_conv = nullptr;
   cudaEvent_t ev_last_conv_ref = nullptr;  // ev_conv of the previous block's slot (history dependency)
@@ -731,6 +733,9 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
+  if (getenv("XLATING_B200_TRACE") != nullptr && atoi(getenv("XLATING_B200_TRACE")) != 0) {
+    if (cudaMalloc(&g->d_trace, sizeof(long long) * 4 * 16384) != cudaSuccess) g->d_trace = nullptr;
+  }
   rc = ensure_ring(g, 4096, false);
   if (rc) return fail(rc);
   *out = g;
@@ -745,6 +750,34 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->s_c) cudaStreamSynchronize(g->s_c);
   if (g->s_c2) cudaStreamSynchronize(g->s_c2);
   if (g->s_out) cudaStreamSynchronize(g->s_out);
+  if (g->d_trace != nullptr && g->trace_ctas > 0) {
+    // timeline of the LAST tiled launch: mean cycles per CTA in each phase
+    std::vector<long long> t((size_t)4 * g->trace_ctas);
+    if (cudaMemcpy(t.data(), g->d_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      double stage = 0, loop = 0, epi = 0;
+      long long first = t[0], last = t[3];
+      for (int i = 0; i < g->trace_ctas; i++) {
+        stage += (double)(t[4 * i + 1] - t[4 * i]);
+        loop += (double)(t[4 * i + 2] - t[4 * i + 1]);
+        epi += (double)(t[4 * i + 3] - t[4 * i + 2]);
+        first = std::min(first, t[4 * i]);
+        last = std::max(last, t[4 * i + 3]);
+      }
+      const double n = g->trace_ctas;
+      fprintf(stderr, "xlating_b200 trace: %d CTAs, mean cycles stage %.0f loop %.0f epilogue %.0f (%.1f%% / %.1f%% / %.1f%%)\n",
+              g->trace_ctas, stage / n, loop / n, epi / n, 100 * stage / (stage + loop + epi),
+              100 * loop / (stage + loop + epi), 100 * epi / (stage + loop + epi));
+      const char *path = getenv("XLATING_B200_TRACE_FILE");
+      if (path != nullptr) {
+        FILE *f = fopen(path, "wb");
+        if (f != nullptr) {
+          fwrite(t.data(), sizeof(long long), t.size(), f);
+          fclose(f);
+        }
+      }
+    }
+    cudaFree(g->d_trace);
+  }
   for (Slot &s : g->slots) {
     slot_free(s);
     cudaEvent_t evs[] = {s.ev_h2d, s.ev_conv, s.ev_phase, s.ev_fir, s.ev_done};
@@ -1034,10 +1067,11 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       }
       if (g->tile_lo == 16)
         fir_tile_cf32_kernel<16><<<ctas, TileShape<16>::kThreads, smem, cs>>>(
-            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out);
+            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out, g->d_trace);
       else
         fir_tile_cf32_kernel<32><<<ctas, TileShape<32>::kThreads, smem, cs>>>(
-            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out);
+            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out, g->d_trace);
+      if (g->d_trace != nullptr) g->trace_ctas = std::min(ctas, 16384);
       if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], cs));
     }
   }

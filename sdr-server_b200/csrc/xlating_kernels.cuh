@@ -449,8 +449,11 @@ template <int LO>
 __global__ void __launch_bounds__(TileShape<LO>::kThreads, TileShape<LO>::kMinCtas)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
                      const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
-                     const float2 *__restrict__ phases, float2 *__restrict__ out) {
+                     const float2 *__restrict__ phases, float2 *__restrict__ out, long long *__restrict__ trace) {
   using S = TileShape<LO>;
+  // optional per-CTA timeline (XLATING_B200_TRACE=1): start, staged, loop done, end
+  long long tr0 = 0, tr1 = 0, tr2 = 0;
+  if (trace != nullptr) tr0 = clock64();
   constexpr int NT = S::kThreads;
   constexpr int KT = S::kKT;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -527,6 +530,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
 
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (trace != nullptr) tr1 = clock64();
 
   float2 acc[T_RK][T_RC];
 #pragma unroll
@@ -616,6 +620,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     }
   }
 
+  if (trace != nullptr) tr2 = clock64();
   // epilogue: derotate with the pre-computed oscillator and store (coalesced in k).
   // The oscillator table is [k][32 clients]: this thread's 8 clients are 64
   // contiguous bytes per output.  The loads of two outputs (and the clients' output
@@ -653,6 +658,13 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
         }
       }
     }
+  }
+  if (trace != nullptr && tid == 0) {
+    long long *t = trace + 4 * (size_t)blockIdx.x;
+    t[0] = tr0;
+    t[1] = tr1;
+    t[2] = tr2;
+    t[3] = clock64();
   }
 }
 
