@@ -306,3 +306,136 @@ def test_group_linearity_full_size(pkg):
     ya, yb, yab = outs
     err = np.max(np.abs((ya + yb) - yab)) / np.max(np.abs(yab))
     assert err < 5e-6, err
+
+
+# ---------------------------------------------------------------------------
+# more edge cases of the batch ABI
+# ---------------------------------------------------------------------------
+def test_group_cs8_and_no_renorm_variant(pkg):
+    """HackRF format through the batch path, and XLG_NO_RENORM = the reference's AVX
+    process_optimized_cf32, which never renormalises the phase (src/xlating.c:336-339)."""
+    rng = np.random.default_rng(37)
+    fs, max_in = 2016000, 32768
+    plan = pkg.client_plan(fs, [48000] * 12, tw=16400)
+    for flags, renorm in ((0, True), (pkg.XLG_NO_RENORM, False)):
+        g = pkg.Group(fs, max_in, flags=flags)
+        taps = pkg.create_low_pass_filter(1.0, fs, 24000, 16400)
+        ids = [g.add_client(p["decimation"], taps, p["center"]) for p in plan]
+        oracles = [po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in) for p in plan]
+        for blk in range(6):
+            x = rand_block(rng, "cs8", max_in)
+            t = g.submit("cs8", x)
+            g.wait(t)
+            for cid, o in zip(ids, oracles):
+                assert_cf32_close(g.output(t, cid), o.process_cf32("cs8", x, renorm=renorm), f"blk {blk} c{cid}")
+        g.close()
+
+
+def test_group_very_long_filter_config5_shape(pkg):
+    """BASELINE configs[4] shape: 61.44 Msps cs16 -> 48 ksps, D = 1280, the server's
+    designer gives T = 15419 taps; 65536 samples per block -> 51/52 outputs."""
+    rng = np.random.default_rng(41)
+    fs, max_in = 61440000, 131072
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 9600)
+    assert len(taps) == 15419
+    g = pkg.Group(fs, max_in)
+    centers = [-20000000, 1234567, 30000000]
+    ids = [g.add_client(1280, taps, c) for c in centers]
+    oracles = [po.OracleFilter(1280, taps, c, fs, max_in) for c in centers]
+    for blk in range(3):
+        x = rand_block(rng, "cs16", max_in)
+        t = g.submit("cs16", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            r = o.process_cf32("cs16", x)
+            assert len(r) in (39, 51, 52)
+            assert_cf32_close(g.output(t, cid), r, f"blk {blk} c{cid}")
+    g.close()
+
+
+def test_group_rejects_oversized_block(pkg, capfd):
+    """the reference overflows its work buffer here (src/xlating.c:353); we refuse"""
+    g = pkg.Group(48000, 1000)
+    g.add_client(5, pkg.create_low_pass_filter(1.0, 48000, 4800, 2000), -12000)
+    with pytest.raises(RuntimeError):
+        g.submit("cu8", np.zeros(1002, dtype=np.uint8))
+    assert "<3>" in capfd.readouterr().err
+    t = g.submit("cu8", np.zeros(1000, dtype=np.uint8))  # still usable
+    g.wait(t)
+    g.close()
+
+
+def test_group_stale_tickets_and_host_ring(pkg):
+    """outputs live XLG_SLOTS tickets by default, host_ring tickets with xlg_create_ex"""
+    rng = np.random.default_rng(43)
+    fs, max_in = 48000, 2000
+    taps = pkg.create_low_pass_filter(1.0, fs, 4800, 2000)
+    for ring in (0, 12):
+        g = pkg.Group(fs, max_in, host_ring=ring)
+        cid = g.add_client(5, taps, -12000)
+        o = po.OracleFilter(5, taps, -12000, fs, max_in)
+        keep = ring if ring else pkg.XLG_SLOTS
+        tickets, refs = [], []
+        for _ in range(keep + 3):
+            x = rand_block(rng, "cu8", max_in)
+            tickets.append(g.submit("cu8", x))
+            refs.append(o.process_cf32("cu8", x))
+        for i, t in enumerate(tickets):
+            if i < 3:
+                with pytest.raises(RuntimeError):
+                    g.wait(t)  # overwritten: -ESTALE
+            else:
+                g.wait(t)
+                assert_cf32_close(g.output(t, cid), refs[i], f"ticket {t}")
+        g.close()
+
+
+def test_group_concurrent_consumers(pkg):
+    """many dsp threads wait on the same tickets concurrently (thread-per-client model)"""
+    import threading
+    rng = np.random.default_rng(47)
+    fs, max_in = 2016000, 32768
+    plan = pkg.client_plan(fs, [48000] * 24, tw=16400)
+    g, ids, oracles = make_group(pkg, fs, max_in, plan)
+    blocks = [rand_block(rng, "cu8", max_in) for _ in range(3)]
+    refs = [[o.process_cf32("cu8", x) for x in blocks] for o in oracles]
+    tickets = [g.submit("cu8", x) for x in blocks]
+    errors = []
+
+    def consumer(idx):
+        try:
+            for b, t in enumerate(tickets):
+                g.wait(t)
+                assert_cf32_close(g.output(t, ids[idx]), refs[idx][b], f"client {idx} block {b}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=consumer, args=(i,)) for i in range(len(ids))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[0]
+    g.close()
+
+
+def test_group_full_size_cfg3_sampled(pkg):
+    """BASELINE configs[2] at full size: 64 clients at 250 ksps on a 10 Msps cs16 stream,
+    1201-tap filters (tw = 20060), 262144-byte blocks."""
+    rng = np.random.default_rng(53)
+    fs, max_in = 10000000, 131072
+    taps = pkg.create_low_pass_filter(1.0, fs, 125000, 20060)
+    assert len(taps) == 1201
+    plan = pkg.client_plan(fs, [250000] * 64, tw=20060)
+    g = pkg.Group(fs, max_in)
+    ids = [g.add_client(p["decimation"], taps, p["center"]) for p in plan]
+    sample = [0, 7, 31, 32, 63]
+    oracles = {c: po.OracleFilter(40, taps, plan[c]["center"], fs, max_in) for c in sample}
+    for blk in range(3):
+        x = rand_block(rng, "cs16", max_in)
+        t = g.submit("cs16", x)
+        g.wait(t)
+        for c in sample:
+            assert_cf32_close(g.output(t, ids[c]), oracles[c].process_cf32("cs16", x), f"blk {blk} c{c}")
+    assert all(g.client_info(c)[1] == 1 for c in ids)
+    g.close()
