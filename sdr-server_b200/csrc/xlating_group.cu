@@ -175,7 +175,8 @@ struct xlg_group {
   float2 *d_taps = nullptr;
   short2 *d_qtaps = nullptr;
   void *d_tile_taps = nullptr;
-  int tile_lo = 32;       // output lanes per warp in the tiled kernel: 32 (128-output tiles) or 16 (64)
+  int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
+  int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
   int *d_order = nullptr;   // clients in oscillator-table order, 32 per group, -1 = padding
   int n_order = 0;
@@ -434,7 +435,7 @@ static int rebuild_layout(xlg_group *g) {
   }
   std::vector<int> members;
   std::vector<float2> tile_taps;  // v1: one float2 per client-tap; v2: two (tr,tr),(ti,ti)
-  const int KT = g->tile_lo * T_RK;
+  const int KT = 128;  // largest tile shape: decides eligibility (smaller shapes need less)
   const size_t smem_fixed = (size_t)T_SMEM_FIXED;
   for (auto &kv : buckets) {
     const uint32_t D = std::get<0>(kv.first);
@@ -724,11 +725,16 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
   // the tiled kernel needs > 48 KiB of dynamic shared memory
   {
     const char *tv = getenv("XLATING_B200_TILE");
-    if (tv != nullptr && atoi(tv) == 16) g->tile_lo = 16;
+    if (tv != nullptr) g->tile_force = atoi(tv);
+    g->fir_sms = g->part.ok ? g->part.big_sms : prop.multiProcessorCount;
   }
-  if (cudaFuncSetAttribute(fir_tile_cf32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+  if (cudaFuncSetAttribute(fir_tile_cf32_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(fir_tile_cf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
@@ -1040,6 +1046,27 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
 
   // ---- FIR ----
   if (!q15 && !g->classes.empty()) {
+    // Tile shape for this launch: the largest thread tile (best FMA : load ratio) that
+    // still yields about two CTAs per SM; fewer clients / outputs -> smaller tiles.
+    static const int kShapes[4][2] = {{32, 4}, {16, 4}, {16, 2}, {16, 1}};
+    int lo = 16, rk = 1;
+    for (const auto &sh : kShapes) {
+      int ctas = 0;
+      for (TileClassHost &ch : g->classes) {
+        const int n_out = ho.n_out[ch.members[0]];
+        if (n_out > 0) ctas += ((n_out + sh[0] * sh[1] - 1) / (sh[0] * sh[1])) * ch.k.n_groups;
+      }
+      if (ctas >= 2 * g->fir_sms) {
+        lo = sh[0];
+        rk = sh[1];
+        break;
+      }
+    }
+    if (g->tile_force > 0) {
+      lo = g->tile_force / 10;
+      rk = g->tile_force % 10;
+    }
+    const int KT = lo * rk;
     TileLaunch P;
     memset(&P, 0, sizeof(P));
     int ctas = 0;
@@ -1052,8 +1079,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       // hist was already advanced above; recover this block's window start
       k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
       k.n_out = n_out;
-      const int KT = g->tile_lo * T_RK;
       k.tiles = (n_out + KT - 1) / KT;
+      k.xs_len = (KT - 1) * k.Dp + k.L;
       k.cta_begin = ctas;
       ctas += k.tiles * k.n_groups;
       smem = std::max(smem, (size_t)T_SMEM_FIXED + ((size_t)k.xs_len + 8) * sizeof(float2));
@@ -1065,12 +1092,20 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
         CU_OK(cudaEventRecord(s.pf[4], cs));
         s.pf_tile = true;
       }
-      if (g->tile_lo == 16)
-        fir_tile_cf32_kernel<16><<<ctas, TileShape<16>::kThreads, smem, cs>>>(
-            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out, g->d_trace);
+      const float2 *tt = (const float2 *)g->d_tile_taps;
+#define XL_LAUNCH_TILE(LO_, RK_)                                                                              \
+  fir_tile_cf32_kernel<LO_, RK_><<<ctas, TileShape<LO_, RK_>::kThreads, smem, cs>>>(P, g->ring, mask, tt,      \
+                                                                                  g->d_members, s.d_phases,  \
+                                                                                  s.d_out, g->d_trace)
+      if (lo == 32 && rk == 4)
+        XL_LAUNCH_TILE(32, 4);
+      else if (lo == 16 && rk == 4)
+        XL_LAUNCH_TILE(16, 4);
+      else if (lo == 16 && rk == 2)
+        XL_LAUNCH_TILE(16, 2);
       else
-        fir_tile_cf32_kernel<32><<<ctas, TileShape<32>::kThreads, smem, cs>>>(
-            P, g->ring, mask, (const float2 *)g->d_tile_taps, g->d_members, s.d_phases, s.d_out, g->d_trace);
+        XL_LAUNCH_TILE(16, 1);
+#undef XL_LAUNCH_TILE
       if (g->d_trace != nullptr) g->trace_ctas = std::min(ctas, 16384);
       if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], cs));
     }

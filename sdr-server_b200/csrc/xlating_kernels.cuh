@@ -352,7 +352,6 @@ fir_generic_q15_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restri
 // ---------------------------------------------------------------------------
 // tiled multi-client FIR (the dominant kernel)
 // ---------------------------------------------------------------------------
-constexpr int T_RK = 4;              // outputs per thread
 constexpr int T_RC = 8;              // clients per thread
 constexpr int T_CG = 32;             // clients per CTA
 constexpr int T_JC = 32;             // flat taps per TMA chunk
@@ -366,23 +365,25 @@ constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
 constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
 constexpr int T_MAX_CLASSES = 8;
 
-// Lane mapping of a warp, LO = number of output lanes:
-//   LO = 32: lane = output column; the warp covers 128 outputs x 8 clients, the CTA
-//            (4 warps) 128 outputs x 32 clients.
+// Shape of the tile a CTA computes.  LO = number of output lanes in a warp, RK =
+// outputs per thread; the thread tile is RK outputs x 8 clients, the CTA tile
+// (LO*RK) outputs x 32 clients.
+//   LO = 32: lane = output column; warp = LO*RK outputs x 8 clients, 4 warps per CTA.
 //   LO = 16: lane = (h, o), o = lane & 15 the output column, h = lane >> 4 the client
-//            half; the warp covers 64 outputs x 16 clients, the CTA (2 warps)
-//            64 outputs x 32 clients.  Both half-warps read the same x (one shared-
-//            memory wavefront instead of two) and tiles are half as large, which
-//            gives the block scheduler twice as many, smaller CTAs to balance.
-// The thread tile is 4 outputs x 8 clients in both cases.
-template <int LO>
+//            half; warp = LO*RK outputs x 16 clients, 2 warps per CTA.  Both half-
+//            warps read the same x (one shared-memory wavefront instead of two).
+// RK = 4 gives the best FMA : shared-load ratio (128 FFMA per 8 loads) and is used
+// whenever it yields enough CTAs to fill the GPU; RK = 2 or 1 trade that ratio for
+// 2x / 4x more (smaller) CTAs when there are few clients or few outputs per block
+// (e.g. 64 clients at 250 ksps: 26 CTAs with RK = 4 cannot occupy 148 SMs).
+template <int LO, int RK>
 struct TileShape {
   static constexpr int kHalves = 32 / LO;                    // client halves per warp
   static constexpr int kWarpClients = kHalves * T_RC;        // 8 or 16
   static constexpr int kWarps = T_CG / kWarpClients;         // 4 or 2
   static constexpr int kThreads = kWarps * 32;               // 128 or 64
-  static constexpr int kKT = LO * T_RK;                      // 128 or 64 outputs per CTA
-  static constexpr int kMinCtas = LO == 32 ? 3 : 6;          // register budget hint
+  static constexpr int kKT = LO * RK;                        // outputs per CTA
+  static constexpr int kMinCtas = (LO == 32 ? 3 : 6) * (RK == 4 ? 1 : 1);
 };
 
 // One class = clients with identical (D, T, window alignment).  "Flat" tap index:
@@ -445,12 +446,12 @@ __device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-template <int LO>
-__global__ void __launch_bounds__(TileShape<LO>::kThreads, TileShape<LO>::kMinCtas)
+template <int LO, int RK>
+__global__ void __launch_bounds__(TileShape<LO, RK>::kThreads, TileShape<LO, RK>::kMinCtas)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
                      const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
                      const float2 *__restrict__ phases, float2 *__restrict__ out, long long *__restrict__ trace) {
-  using S = TileShape<LO>;
+  using S = TileShape<LO, RK>;
   // optional per-CTA timeline (XLATING_B200_TRACE=1): start, staged, loop done, end
   long long tr0 = 0, tr1 = 0, tr2 = 0;
   if (trace != nullptr) tr0 = clock64();
@@ -532,16 +533,15 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   __syncthreads();
   if (trace != nullptr) tr1 = clock64();
 
-  float2 acc[T_RK][T_RC];
+  float2 acc[RK][T_RC];
 #pragma unroll
-  for (int i = 0; i < T_RK; i++)
+  for (int i = 0; i < RK; i++)
 #pragma unroll
     for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
 
-  const float2 *xb0 = xs + o * Dp;
-  const float2 *xb1 = xb0 + LO * Dp;
-  const float2 *xb2 = xb1 + LO * Dp;
-  const float2 *xb3 = xb2 + LO * Dp;
+  const float2 *xb[RK];
+#pragma unroll
+  for (int i = 0; i < RK; i++) xb[i] = xs + (o + LO * i) * Dp;
 
   for (int ch = 0; ch < nchunks; ch++) {
     const int s = ch % T_STAGES;
@@ -550,46 +550,18 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       const int len = min(T_JC, L - ch * T_JC);
       const float4 *tp = reinterpret_cast<const float4 *>(ts + s * T_CHUNK_F2 + cbase);
       const int fbase = ch * T_JC;
-#ifdef XL_TILE_EXPLICIT_PREFETCH
-      // operands are fetched one tap ahead of the FMAs that consume them (the
-      // fetch past the end of a chunk reads valid shared memory and is discarded)
-      float2 xn[T_RK];
-      float4 tn[T_RC / 2];
-      xn[0] = xb0[fbase];
-      xn[1] = xb1[fbase];
-      xn[2] = xb2[fbase];
-      xn[3] = xb3[fbase];
-#pragma unroll
-      for (int q = 0; q < T_RC / 2; q++) tn[q] = tp[q];
-#endif
 #pragma unroll 1
       for (int f = 0; f < len; f += T_UNROLL) {
 #pragma unroll
         for (int u = 0; u < T_UNROLL; u++) {
-          float2 x[T_RK];
+          float2 x[RK];
           float4 tq[T_RC / 2];
-#ifdef XL_TILE_EXPLICIT_PREFETCH
 #pragma unroll
-          for (int i = 0; i < T_RK; i++) x[i] = xn[i];
-#pragma unroll
-          for (int q = 0; q < T_RC / 2; q++) tq[q] = tn[q];
-          const int fn = f + u + 1;
-          xn[0] = xb0[fbase + fn];
-          xn[1] = xb1[fbase + fn];
-          xn[2] = xb2[fbase + fn];
-          xn[3] = xb3[fbase + fn];
-#pragma unroll
-          for (int q = 0; q < T_RC / 2; q++) tn[q] = tp[fn * (T_CG / 2) + q];
-#else
-          x[0] = xb0[fbase + f + u];
-          x[1] = xb1[fbase + f + u];
-          x[2] = xb2[fbase + f + u];
-          x[3] = xb3[fbase + f + u];
+          for (int i = 0; i < RK; i++) x[i] = xb[i][fbase + f + u];
 #pragma unroll
           for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
-#endif
 #pragma unroll
-          for (int i = 0; i < T_RK; i++) {
+          for (int i = 0; i < RK; i++) {
 #pragma unroll
             for (int q = 0; q < T_RC / 2; q++) {
               float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
@@ -634,17 +606,18 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     }
     const float4 *pt =
         reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride + cbase);
+    constexpr int EB = RK >= 2 ? 2 : 1;  // outputs whose table loads are in flight together
 #pragma unroll
-    for (int i2 = 0; i2 < T_RK; i2 += 2) {
-      float4 ph[2][T_RC / 2];
+    for (int i2 = 0; i2 < RK; i2 += EB) {
+      float4 ph[EB][T_RC / 2];
 #pragma unroll
-      for (int ii = 0; ii < 2; ii++) {
+      for (int ii = 0; ii < EB; ii++) {
         const int k = min(k0 + o + LO * (i2 + ii), n_out - 1);  // clamped: always a valid row
 #pragma unroll
         for (int q = 0; q < T_RC / 2; q++) ph[ii][q] = __ldg(pt + (size_t)k * 16 + q);
       }
 #pragma unroll
-      for (int ii = 0; ii < 2; ii++) {
+      for (int ii = 0; ii < EB; ii++) {
         const int i = i2 + ii;
         const int k = k0 + o + LO * i;
         if (k >= n_out) continue;
