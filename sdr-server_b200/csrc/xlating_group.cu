@@ -442,7 +442,10 @@ static int rebuild_layout(xlg_group *g) {
     const size_t T = std::get<1>(kv.first);
     std::vector<int> &ids = kv.second;
     if ((int)ids.size() < kTileMinClients) continue;
-    const int Dp = (int)(D | 1u);
+    // natural layout when the lane stride D is at most 2-way bank conflicting
+    const unsigned g16 = (D % 16 == 0) ? 16u : (D % 8 == 0) ? 8u : (D % 4 == 0) ? 4u : (D % 2 == 0) ? 2u : 1u;
+    const bool natural = g16 <= 2 && !getenv("XLATING_B200_SKEWED");
+    const int Dp = natural ? (int)D : (int)(D | 1u);
     const size_t q_last = (T - 1) / D, r_last = (T - 1) % D;
     const int L = (int)(((q_last * Dp + r_last + 1) + 7) / 8 * 8);
     const int xs_len = (KT - 1) * Dp + L;
@@ -460,6 +463,7 @@ static int rebuild_layout(xlg_group *g) {
     ch.k.xs_len = xs_len;
     ch.k.n_groups = (int)((ids.size() + T_CG - 1) / T_CG);
     ch.k.n_members = (int)ids.size();
+    ch.k.natural = natural ? 1 : 0;
     ch.k.members_off = (int)members.size();
     ch.k.taps_off = (long long)tile_taps.size();
     for (int gi = 0; gi < ch.k.n_groups; gi++) {
@@ -1048,7 +1052,9 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   if (!q15 && !g->classes.empty()) {
     // Tile shape for this launch: the largest thread tile (best FMA : load ratio) that
     // still yields about two CTAs per SM; fewer clients / outputs -> smaller tiles.
-    static const int kShapes[4][2] = {{32, 4}, {16, 4}, {16, 2}, {16, 1}};
+    // (the natural input layout is 2-way bank conflicting for even D, which 16 output
+    // lanes absorb and 32 would not, so the production shapes all have LO = 16)
+    static const int kShapes[3][2] = {{16, 4}, {16, 2}, {16, 1}};
     int lo = 16, rk = 1;
     for (const auto &sh : kShapes) {
       int ctas = 0;
@@ -1083,7 +1089,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       k.xs_len = (KT - 1) * k.Dp + k.L;
       k.cta_begin = ctas;
       ctas += k.tiles * k.n_groups;
-      smem = std::max(smem, (size_t)T_SMEM_FIXED + ((size_t)k.xs_len + 8) * sizeof(float2));
+      smem = std::max(smem, (size_t)T_SMEM_FIXED + ((size_t)k.xs_len + 10) * sizeof(float2));
       P.cls[P.n_classes++] = k;
       s.tile_macs += (uint64_t)k.tiles * KT * (uint64_t)k.L * (uint64_t)ch.members.size();
     }
