@@ -439,3 +439,71 @@ def test_group_full_size_cfg3_sampled(pkg):
             assert_cf32_close(g.output(t, ids[c]), oracles[c].process_cf32("cs16", x), f"blk {blk} c{c}")
     assert all(g.client_info(c)[1] == 1 for c in ids)
     g.close()
+
+
+def test_dropin_many_filters_thread_per_client(pkg):
+    """The unmodified reference server: one filter + one dsp thread per client, all
+    processing copies of the same blocks concurrently (src/dsp_worker.c:41-88)."""
+    import threading
+    rng = np.random.default_rng(59)
+    fs, max_in, n_clients = 2016000, 65536, 24
+    plan = pkg.client_plan(fs, [48000 if c % 3 else 96000 for c in range(n_clients)])
+    blocks = [rand_block(rng, "cu8", max_in) for _ in range(4)]
+    filters, refs = [], []
+    for p in plan:
+        taps = pkg.create_low_pass_filter(1.0, fs, p["cutoff"], p["tw"])
+        filters.append(pkg.XlatingFilter(p["decimation"], taps, p["center"], fs, max_in))
+        o = po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in)
+        refs.append([o.process_cf32("cu8", x) for x in blocks])
+    errors = []
+
+    def dsp_thread(i):
+        try:
+            for b, x in enumerate(blocks):
+                own_copy = x.copy()  # queue_put memcpy'd a private copy per client (src/queue.c:114)
+                assert_cf32_close(filters[i].process_cf32("cu8", own_copy), refs[i][b], f"client {i} block {b}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=dsp_thread, args=(i,)) for i in range(n_clients)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+    for f in filters:
+        f.close()
+
+
+def test_group_empty_blocks_and_client_churn(pkg):
+    """zero-length blocks, removing every client, re-adding, growing the arenas"""
+    rng = np.random.default_rng(61)
+    fs, max_in = 2016000, 32768
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 16400)
+    g = pkg.Group(fs, max_in)
+    t = g.submit("cu8", np.zeros(0, dtype=np.uint8))  # no clients, no data
+    g.wait(t)
+    ids = [g.add_client(42, taps, 1000 * c) for c in range(3)]
+    oracles = [po.OracleFilter(42, taps, 1000 * c, fs, max_in) for c in range(3)]
+    for n in (0, max_in, 0, 2, max_in):
+        x = rand_block(rng, "cu8", n)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"n={n}")
+    for cid in ids:
+        g.remove_client(cid)
+    assert g.client_count() == 0
+    t = g.submit("cu8", rand_block(rng, "cu8", max_in))  # stream advances with nobody listening
+    g.wait(t)
+    # 40 new clients (arenas and tables grow); they start with zero history at the current position
+    plan = pkg.client_plan(fs, [48000] * 40, tw=16400)
+    ids = [g.add_client(p["decimation"], taps, p["center"]) for p in plan]
+    oracles = [po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in) for p in plan]
+    for blk in range(3):
+        x = rand_block(rng, "cu8", max_in)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"blk {blk} c{cid}")
+    g.close()
