@@ -657,9 +657,11 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   }
   if (trace != nullptr && tid == 0) {
     long long *t = trace + 4 * (size_t)blockIdx.x;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     t[0] = tr0;
     t[1] = tr1;
-    t[2] = tr2;
+    t[2] = (tr2 & 0x0000ffffffffffffll) | ((long long)smid << 48);  // smid in the top 16 bits
     t[3] = clock64();
   }
 }
