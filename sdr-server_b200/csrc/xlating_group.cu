@@ -15,9 +15,10 @@
  *   per slot (XLG_SLOTS in flight): raw input staging, BlkInfo, per-output
  *                    oscillator table, output arena (+ pinned host mirrors)
  *
- * Streams: s_in (H2D), s_ph (oscillator pre-pass chain), s_c (convert + FIR),
- * s_out (D2H); events order them per block so block b+1's copy and pre-pass
- * overlap block b's FIR.
+ * Streams: s_in (H2D), s_ph (oscillator pre-pass chain), s_c / s_c2 (convert + FIR,
+ * alternating by block), s_out (D2H); events order them per block so block b+1's
+ * copy and pre-pass overlap block b's FIR and consecutive FIRs overlap each other.
+ * With XLG_SM_PARTITION s_ph lives in an 8-SM green context and s_c / s_c2 in the rest.
  *
  * The reference's per-client dsp loop this replaces: src/dsp_worker.c:41-88 calling
  * src/xlating.c:384-414 -> :52-83 once per client per block.
@@ -61,7 +62,7 @@ using namespace xl;
 namespace {
 
 constexpr int kTileMinClients = 8;     // smaller aligned classes go to the generic kernel
-constexpr int kTileMinOutputs = 48;    // per block; below this a 128-output tile is mostly idle
+constexpr int kTileMinOutputs = 12;    // per block; below this even a 16-output tile is mostly idle
 constexpr int kTileMaxSmem = 200 * 1024;
 
 struct HostClient {
@@ -178,6 +179,7 @@ struct xlg_group {
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
   int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
+  float2 *d_member_incr = nullptr;  // oscillator step per member slot (same indexing as d_members)
   int *d_order = nullptr;   // clients in oscillator-table order, 32 per group, -1 = padding
   int n_order = 0;
   size_t phase_cap = 0;     // float2 per slot oscillator table
@@ -195,7 +197,6 @@ struct xlg_group {
   long long *d_trace = nullptr;  // XLATING_B200_TRACE=1: per-CTA timeline of the tiled kernel
   int trace_ctas = 0;
   std::atomic<int64_t> next_ticket{0};
-  cudaEvent_t ev_last_conv = nullptr;
   cudaEvent_t ev_last_conv_ref = nullptr;  // ev_conv of the previous block's slot (history dependency)
   bool have_last_conv = false;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -434,6 +435,7 @@ static int rebuild_layout(xlg_group *g) {
     if (!(g->flags & XLG_FORCE_GENERIC) && settled) buckets[std::make_tuple(h.D, h.T, h.hist)].push_back(i);
   }
   std::vector<int> members;
+  std::vector<float2> member_incr;
   std::vector<float2> tile_taps;  // v1: one float2 per client-tap; v2: two (tr,tr),(ti,ti)
   const int KT = 128;  // largest tile shape: decides eligibility (smaller shapes need less)
   const size_t smem_fixed = (size_t)T_SMEM_FIXED;
@@ -473,10 +475,12 @@ static int rebuild_layout(xlg_group *g) {
         const size_t idx = (size_t)gi * T_CG + m;
         if (idx >= ids.size()) {
           members.push_back(-1);
+          member_incr.push_back(make_float2(1.f, 0.f));
           continue;
         }
         const int id = ids[idx];
         members.push_back(g->clients[id].out_off);  // the kernel only needs the output row
+        member_incr.push_back(make_float2(g->clients[id].incr_re, g->clients[id].incr_im));
         g->clients[id].kind = 1;
         const HostClient &h = g->clients[id];
         for (size_t j = 0; j < T; j++) {
@@ -494,13 +498,18 @@ static int rebuild_layout(xlg_group *g) {
   });
   if (g->d_tile_taps) cudaFree(g->d_tile_taps);
   if (g->d_members) cudaFree(g->d_members);
+  if (g->d_member_incr) cudaFree(g->d_member_incr);
   g->d_tile_taps = nullptr;
   g->d_members = nullptr;
+  g->d_member_incr = nullptr;
   if (!tile_taps.empty()) {
     CU_OK(cudaMalloc(&g->d_tile_taps, tile_taps.size() * sizeof(float2)));
     CU_OK(cudaMemcpy(g->d_tile_taps, tile_taps.data(), tile_taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU_OK(cudaMalloc(&g->d_members, members.size() * sizeof(int)));
     CU_OK(cudaMemcpy(g->d_members, members.data(), members.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU_OK(cudaMalloc(&g->d_member_incr, member_incr.size() * sizeof(float2)));
+    CU_OK(cudaMemcpy(g->d_member_incr, member_incr.data(), member_incr.size() * sizeof(float2),
+                     cudaMemcpyHostToDevice));
   }
 
   // 3b. oscillator-table order: tile classes (the order the tiled kernel walks them),
@@ -511,6 +520,7 @@ static int rebuild_layout(xlg_group *g) {
     for (TileClassHost &ch : g->classes) {
       int cap = 0;
       for (int id : ch.members) cap = std::max(cap, g->clients[id].out_cap);
+      cap = cap / 2 + 1;  // only even outputs are tabulated
       ch.k.ph_base = (long long)table;
       ch.k.ph_stride = cap * 32;
       for (int gi = 0; gi < ch.k.n_groups; gi++) {
@@ -532,6 +542,7 @@ static int rebuild_layout(xlg_group *g) {
     for (size_t base = 0; base < loose.size(); base += 32) {
       int cap = 0;
       for (size_t m = base; m < std::min(base + 32, loose.size()); m++) cap = std::max(cap, g->clients[loose[m]].out_cap);
+      cap = cap / 2 + 1;
       for (size_t m = 0; m < 32; m++) {
         if (base + m < loose.size()) {
           g->clients[loose[base + m]].ph_off = (int)(table + m);
@@ -724,7 +735,6 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     for (int i = 0; i < 8; i++)
       if (cudaEventCreate(&s.pf[i]) != cudaSuccess) return fail(-EIO);
   }
-  if (cudaEventCreateWithFlags(&g->ev_last_conv, cudaEventDisableTiming) != cudaSuccess) return fail(-EIO);
   if (cudaEventCreate(&g->ev_t0) != cudaSuccess || cudaEventCreate(&g->ev_t1) != cudaSuccess) return fail(-EIO);
   // the tiled kernel needs > 48 KiB of dynamic shared memory
   {
@@ -802,7 +812,6 @@ extern "C" void xlg_destroy(xlg_group *g) {
     if (h.h_qout) cudaFreeHost(h.h_qout);
   }
   for (void *p : g->retired_host) cudaFreeHost(p);
-  if (g->ev_last_conv) cudaEventDestroy(g->ev_last_conv);
   if (g->ev_t0) cudaEventDestroy(g->ev_t0);
   if (g->ev_t1) cudaEventDestroy(g->ev_t1);
   if (g->ring) cudaFree(g->ring);
@@ -812,6 +821,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_qtaps) cudaFree(g->d_qtaps);
   if (g->d_tile_taps) cudaFree(g->d_tile_taps);
   if (g->d_members) cudaFree(g->d_members);
+  if (g->d_member_incr) cudaFree(g->d_member_incr);
   if (g->d_order) cudaFree(g->d_order);
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_ph) cudaStreamDestroy(g->s_ph);
@@ -1105,7 +1115,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       const float2 *tt = (const float2 *)g->d_tile_taps;
 #define XL_LAUNCH_TILE(LO_, RK_)                                                                              \
   fir_tile_cf32_kernel<LO_, RK_><<<ctas, TileShape<LO_, RK_>::kThreads, smem, cs>>>(P, g->ring, mask, tt,      \
-                                                                                  g->d_members, s.d_phases,  \
+                                                                                  g->d_members,              \
+                                                                                  g->d_member_incr, s.d_phases, \
                                                                                   s.d_out, g->d_trace)
       if (lo == 32 && rk == 4)
         XL_LAUNCH_TILE(32, 4);

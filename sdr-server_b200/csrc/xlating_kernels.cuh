@@ -54,7 +54,7 @@ struct ClientDev {
   int active;
   int kind;               // 0 = generic kernel, 1 = tiled kernel
   int renorm;             // 1 = native behaviour (:73), 0 = AVX behaviour (:336-339)
-  int ph_off;             // cf32 oscillator table: phase of output k lives at phases[ph_off + 32*k]
+  int ph_off;             // cf32 oscillator table: phase of EVEN output k lives at phases[ph_off + 32*(k/2)]
 };
 
 struct BlkInfo {
@@ -142,7 +142,7 @@ constexpr int P_QTHREADS = 64;  // Q15 variant (one thread per client)
 
 // Oscillator table layout: clients are taken in "table order" (tile classes first,
 // in the order the tiled kernel walks them, then the generic clients), 32 per
-// group; group g stores phase(k, lane) at phases[base_g + 32*k + lane].  Lane l of
+// group; group g stores phase(2m, lane) at phases[base_g + 32*m + lane].  Lane l of
 // the warp owns client order[32*g + l] and walks its recursion sequentially -- the
 // dependent chain (2 fp32 ops, 10.75 cycles per output measured on B200) is the
 // only thing on the critical path: the per-output store is one coalesced 256-byte
@@ -170,13 +170,25 @@ phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, Blk
   float2 p = d->phase;
   const float2 inc = d->incr;
   float2 *dst = phases + d->ph_off;
-  // unrolled 32x: a global store keeps its source registers reserved until the LSU
-  // has read them (a long-scoreboard release, ~100+ cycles); with a short unroll the
-  // recursion stalls on that write-after-read hazard when the registers come round
-#pragma unroll 32
-  for (int k = 0; k < n_out; k++) {
-    dst[(size_t)k * 32] = p;   // phase of output k
-    p = cmul_unfused(p, inc);  // src/xlating.c:71
+  // Only the phases of EVEN outputs are stored; a consumer derives an odd output's
+  // phase with the same single unfused multiply the recursion itself performs
+  // (phase_{k+1} = phase_k * incr), so nothing changes numerically while the store
+  // rate and the table halve.  That matters because a lone warp can only keep ~32
+  // stores in flight: at one 256-byte store per output the recursion ran at 16.7
+  // cycles/output against its 10.75-cycle dependent chain.
+  // Unrolled 16 pairs: a global store keeps its source registers reserved until the
+  // LSU has read them (a long-scoreboard release, ~100+ cycles); with a short unroll
+  // the recursion stalls on that write-after-read hazard when the registers come round.
+  const int n_pairs = n_out >> 1;
+#pragma unroll 16
+  for (int m = 0; m < n_pairs; m++) {
+    dst[(size_t)m * 32] = p;   // phase of output 2m
+    p = cmul_unfused(p, inc);  // src/xlating.c:71 (output 2m+1)
+    p = cmul_unfused(p, inc);
+  }
+  if (n_out & 1) {
+    dst[(size_t)n_pairs * 32] = p;  // last (even-indexed) output
+    p = cmul_unfused(p, inc);
   }
   if (n_out > 0 && d->renorm) {
     // src/xlating.c:73.  glibc's hypotf is (float)sqrt((double)x*x + (double)y*y)
@@ -282,7 +294,8 @@ fir_generic_cf32_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restr
     if (lane == i) mine = acc[i];
   const int k = k0 + lane;
   if (lane < G_OPW && k < b.n_out) {
-    const float2 ph = phases[d->ph_off + (size_t)k * 32];
+    float2 ph = phases[d->ph_off + (size_t)(k >> 1) * 32];
+    if (k & 1) ph = cmul_unfused(ph, d->incr);     // odd outputs: one step from the stored even phase
     out[d->out_off + k] = cmul_unfused(mine, ph);  // src/xlating.c:70
   }
 }
@@ -383,7 +396,7 @@ struct TileShape {
   static constexpr int kWarps = T_CG / kWarpClients;         // 4 or 2
   static constexpr int kThreads = kWarps * 32;               // 128 or 64
   static constexpr int kKT = LO * RK;                        // outputs per CTA
-  static constexpr int kMinCtas = (LO == 32 ? 3 : 6) * (RK == 4 ? 1 : 1);
+  static constexpr int kMinCtas = LO == 32 ? 3 : 6;          // register budget hint for ptxas
 };
 
 // One class = clients with identical (D, T, window alignment).  "Flat" tap index:
@@ -450,7 +463,8 @@ template <int LO, int RK>
 __global__ void __launch_bounds__(TileShape<LO, RK>::kThreads, TileShape<LO, RK>::kMinCtas)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
                      const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
-                     const float2 *__restrict__ phases, float2 *__restrict__ out, long long *__restrict__ trace) {
+                     const float2 *__restrict__ member_incr, const float2 *__restrict__ phases,
+                     float2 *__restrict__ out, long long *__restrict__ trace) {
   using S = TileShape<LO, RK>;
   // optional per-CTA timeline (XLATING_B200_TRACE=1): start, staged, loop done, end
   long long tr0 = 0, tr1 = 0, tr2 = 0;
@@ -622,11 +636,19 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   // row offsets) are in flight together before the first use.
   if (warp_active) {
     int off[T_RC];
+    float4 inc[T_RC / 2];  // oscillator steps of the 8 clients, (re, im) pairs
     {
       const int *mo = member_off + K.members_off + grp * T_CG + cbase;
 #pragma unroll
       for (int c = 0; c < T_RC; c++) off[c] = __ldg(mo + c);  // -1 = padding slot
+      const float4 *mi = reinterpret_cast<const float4 *>(member_incr + K.members_off + grp * T_CG + cbase);
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++) inc[q] = __ldg(mi + q);
     }
+    // only even outputs' phases are tabulated; an odd output advances the stored
+    // phase by one step, exactly as the reference's recursion does (src/xlating.c:71).
+    // k = k0 + o + LO*i has the parity of o (k0 and LO are even): uniform per lane.
+    const bool odd = (o & 1) != 0;
     const float4 *pt =
         reinterpret_cast<const float4 *>(phases + K.ph_base + (long long)grp * K.ph_stride + cbase);
     constexpr int EB = RK >= 2 ? 2 : 1;  // outputs whose table loads are in flight together
@@ -637,7 +659,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       for (int ii = 0; ii < EB; ii++) {
         const int k = min(k0 + o + LO * (i2 + ii), n_out - 1);  // clamped: always a valid row
 #pragma unroll
-        for (int q = 0; q < T_RC / 2; q++) ph[ii][q] = __ldg(pt + (size_t)k * 16 + q);
+        for (int q = 0; q < T_RC / 2; q++) ph[ii][q] = __ldg(pt + (size_t)(k >> 1) * 16 + q);
       }
 #pragma unroll
       for (int ii = 0; ii < EB; ii++) {
@@ -646,11 +668,13 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
         if (k >= n_out) continue;
 #pragma unroll
         for (int q = 0; q < T_RC / 2; q++) {
-          if (off[2 * q] >= 0)
-            out[off[2 * q] + k] =
-                cmul_unfused(acc[i][2 * q], make_float2(ph[ii][q].x, ph[ii][q].y));  // src/xlating.c:70
-          if (off[2 * q + 1] >= 0)
-            out[off[2 * q + 1] + k] = cmul_unfused(acc[i][2 * q + 1], make_float2(ph[ii][q].z, ph[ii][q].w));
+          float2 p0 = make_float2(ph[ii][q].x, ph[ii][q].y), p1 = make_float2(ph[ii][q].z, ph[ii][q].w);
+          if (odd) {
+            p0 = cmul_unfused(p0, make_float2(inc[q].x, inc[q].y));
+            p1 = cmul_unfused(p1, make_float2(inc[q].z, inc[q].w));
+          }
+          if (off[2 * q] >= 0) out[off[2 * q] + k] = cmul_unfused(acc[i][2 * q], p0);  // src/xlating.c:70
+          if (off[2 * q + 1] >= 0) out[off[2 * q + 1] + k] = cmul_unfused(acc[i][2 * q + 1], p1);
         }
       }
     }
