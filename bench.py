@@ -58,6 +58,10 @@ def workload(name, taps_mode):
     elif name == "c512":
         fs, fmt, rates = 2016000, "cu8", [48000] * 512
         desc = "cfg4 per-GPU shape: 512 clients, 2.016 Msps cu8 -> 48 ksps"
+    elif name == "cfg5shard":
+        # one GPU's share of BASELINE configs[4]: 61.44 Msps cs16, 4096 clients / 8 GPUs at 48 ksps
+        fs, fmt, rates = 61440000, "cs16", [48000] * 512
+        desc = "cfg5 per-GPU shard: 512 of 4096 clients, 61.44 Msps cs16 -> 48 ksps (15419 taps)"
     elif name == "c1000":
         fs, fmt, rates = 2016000, "cu8", [48000] * 1000
         desc = "target row: 1000 clients, 2.016 Msps cu8 -> 48 ksps"

@@ -80,6 +80,7 @@ struct HostClient {
   int out_off = 0, out_cap = 0;
   int taps_off = 0;
   int ph_off = 0;
+  bool tile_ineligible = false;  // its class cannot use the tiled kernel (shared memory, too few outputs)
 };
 
 struct Slot {
@@ -432,12 +433,13 @@ static int rebuild_layout(xlg_group *g) {
     h.kind = 0;
     const long long first = g->S - h.hist;
     const bool settled = (h.zero_before == 0 && g->S < (long long)g->ring_cap / 2) || h.zero_before <= first;
+    h.tile_ineligible = false;
     if (!(g->flags & XLG_FORCE_GENERIC) && settled) buckets[std::make_tuple(h.D, h.T, h.hist)].push_back(i);
   }
   std::vector<int> members;
   std::vector<float2> member_incr;
   std::vector<float2> tile_taps;  // v1: one float2 per client-tap; v2: two (tr,tr),(ti,ti)
-  const int KT = 128;  // largest tile shape: decides eligibility (smaller shapes need less)
+  const int KT = 64;  // largest production tile shape: decides eligibility (smaller shapes need less)
   const size_t smem_fixed = (size_t)T_SMEM_FIXED;
   for (auto &kv : buckets) {
     const uint32_t D = std::get<0>(kv.first);
@@ -453,8 +455,12 @@ static int rebuild_layout(xlg_group *g) {
     const int xs_len = (KT - 1) * Dp + L;
     const size_t smem = smem_fixed + ((size_t)xs_len + 8) * sizeof(float2);
     const size_t typical_out = g->max_input_len / 2 / D;
-    if (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs) continue;
-    if ((int)g->classes.size() >= T_MAX_CLASSES) continue;
+    if (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs ||
+        (int)g->classes.size() >= T_MAX_CLASSES) {
+      // stays on the generic kernel for good: do not re-derive the layout every block
+      for (int id : ids) g->clients[id].tile_ineligible = true;
+      continue;
+    }
     TileClassHost ch;
     memset(&ch.k, 0, sizeof(ch.k));
     ch.T = T;
@@ -928,7 +934,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   if (!g->dirty && !q15 && g->n_generic > 0 && !(g->flags & XLG_FORCE_GENERIC)) {
     std::map<std::tuple<uint32_t, size_t, long long>, int> cnt;
     for (const HostClient &h : g->clients)
-      if (h.active && h.kind == 0 && h.zero_before <= g->S - h.hist) cnt[std::make_tuple(h.D, h.T, h.hist)]++;
+      if (h.active && h.kind == 0 && !h.tile_ineligible && h.zero_before <= g->S - h.hist)
+        cnt[std::make_tuple(h.D, h.T, h.hist)]++;
     for (auto &kv : cnt)
       if (kv.second >= kTileMinClients) {
         g->dirty = true;
@@ -1085,6 +1092,11 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     if (g->tile_force > 0) {
       lo = g->tile_force / 10;
       rk = g->tile_force % 10;
+      for (TileClassHost &ch : g->classes)  // an experiment must not overflow shared memory
+        if ((size_t)T_SMEM_FIXED + ((size_t)(lo * rk - 1) * ch.k.Dp + ch.k.L + 10) * sizeof(float2) > (size_t)kTileMaxSmem) {
+          lo = 16;
+          rk = 1;
+        }
     }
     const int KT = lo * rk;
     TileLaunch P;
