@@ -58,6 +58,11 @@ def workload(name, taps_mode):
     elif name == "c512":
         fs, fmt, rates = 2016000, "cu8", [48000] * 512
         desc = "cfg4 per-GPU shape: 512 clients, 2.016 Msps cu8 -> 48 ksps"
+    elif name == "cfg5":
+        # BASELINE configs[4]: ONE 61.44 Msps wideband input, NCCL-broadcast to all GPUs,
+        # 4096 clients at 48 ksps sharded over the GPUs (client c -> rank c mod N)
+        fs, fmt, rates = 61440000, "cs16", [48000] * 4096
+        desc = "cfg5: single 61.44 Msps cs16 input NCCL-broadcast, 4096 clients at 48 ksps sharded c mod N"
     elif name == "cfg5shard":
         # one GPU's share of BASELINE configs[4]: 61.44 Msps cs16, 4096 clients / 8 GPUs at 48 ksps
         fs, fmt, rates = 61440000, "cs16", [48000] * 512
@@ -234,6 +239,132 @@ def job_throughput_msps(block_samples, steps, world, elapsed_ms_max):
     return world * block_samples * steps / (elapsed_ms_max * 1e-3) / 1e6
 
 
+def run_broadcast_workload(args, wl, config, rank, world, local_rank):
+    """BASELINE configs[4]: one wideband stream, every GPU needs every block.  Rank 0
+    owns the stream (synthetic blocks in its HBM, or in pinned host memory for e2e) and
+    NCCL-broadcasts each block; every rank decimates its own shard of the clients from
+    the received buffer (xlg_wait_stream + XLG_INPUT_DEVICE: the kernel consumes the
+    NCCL receive buffer directly, no staging copy).  Strong scaling: the job's work is
+    fixed, `value` is the input rate of the ONE stream."""
+    import torch
+    import torch.distributed as dist
+
+    pkg = importlib.import_module("sdr-server_b200")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    plan = wl["plan"][rank::world]
+    fmt_code = pkg.FMT[wl["fmt"]]
+    taps = pkg.create_low_pass_filter(1.0, wl["fs"], plan[0]["cutoff"], plan[0]["tw"])
+    config["taps_len"] = [len(taps)]
+    config["parallelism"] = f"clients sharded c mod {world}; input NCCL-broadcast from rank 0"
+    config["streams"] = "ONE wideband stream for the whole job"
+    config["l2"] = "64 distinct source blocks (16.8 MB) on rank 0; receive ring of 4 buffers per rank"
+    config["clients_per_gpu"] = len(plan)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_group(flags):
+        g = pkg.Group(wl["fs"], wl["block_elems"], device=local_rank, flags=flags)
+        return g, [g.add_client(p["decimation"], taps, p["center"]) for p in plan]
+
+    n_src = 64
+    src_host = synth_blocks(wl["fmt"], n_src, wl["block_elems"], seed=stream_seed(0))
+    nbytes = src_host[0].nbytes
+    src_dev = torch.from_numpy(src_host.view(np.uint8).reshape(n_src, -1)).to(dev) if rank == 0 else None
+    pinned = torch.from_numpy(src_host.view(np.uint8).reshape(n_src, -1)).pin_memory() if rank == 0 else None
+    ring = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(pkg.XLG_SLOTS)]
+    stream = torch.cuda.current_stream()
+
+    def pump(g, steps, from_host):
+        """broadcast + submit `steps` blocks, keeping at most XLG_SLOTS-1 tickets in flight"""
+        pend = []
+        for i in range(steps):
+            buf = ring[i % len(ring)]
+            if len(pend) >= len(ring) - 1:
+                g.wait(pend.pop(0))  # the block that used this buffer has been converted
+            if rank == 0:
+                buf.copy_(pinned[i % n_src] if from_host else src_dev[i % n_src], non_blocking=True)
+            if world > 1:
+                dist.broadcast(buf, src=0)
+            g.wait_stream(stream.cuda_stream)
+            pend.append(g.submit_ptr(fmt_code, buf.data_ptr(), wl["block_elems"], pkg.XLG_INPUT_DEVICE))
+        for t in pend:
+            g.wait(t)
+
+    g, ids = make_group(pkg.XLG_OUT_DEVICE)
+    pump(g, args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    g.timer_start()
+    pump(g, args.steps, False)
+    ms = g.timer_stop()
+    barrier()
+    ms_max = max_over_ranks(ms, world, "cuda")
+    g.profile_enable(True)
+    g.profile_read(reset=True)
+    pump(g, min(args.steps, 50), False)
+    g.profile_enable(False)
+    prof = g.profile_read(reset=True)
+    kinds = sorted({g.client_info(c)[1] for c in ids})
+    g.close()
+    value = wl["block_samples"] * args.steps / (ms_max * 1e-3) / 1e6  # ONE stream
+
+    g2, ids2 = make_group(0)
+    pump(g2, args.warmup, True)
+    e2e_steps = min(args.steps, 100)
+    barrier()
+    t0 = time.perf_counter()
+    pump(g2, e2e_steps, True)
+    torch.cuda.synchronize()
+    wall = max_over_ranks(time.perf_counter() - t0, world, "cuda")
+    barrier()
+    g2.close()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return 0
+    n_out_per_block = len(wl["plan"]) * (wl["block_samples"] // plan[0]["decimation"])
+    e2e = {"value": wl["block_samples"] * e2e_steps / wall / 1e6, "unit": "MS/s",
+           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(n_out_per_block * 8), "steps": e2e_steps,
+           "timing": "host wall clock; rank 0 copies the block from pinned host memory, NCCL broadcast, every rank "
+                     "copies its clients' outputs back"}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    k_ms = prof["fir_generic_ms"] / max(prof["fir_generic_launches"], 1)
+    if prof["fir_tile_launches"] > 0:
+        k_ms = prof["fir_tile_ms"] / prof["fir_tile_launches"]
+    algo_bytes = nbytes + 8 * n_out_per_block / world
+    algo_fma = 4.0 * prof["algo_macs"] / max(prof["blocks"], 1)
+    roof = {"bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+            "kernel": "fir_generic_cf32_kernel (per rank)" if prof["fir_tile_launches"] == 0 else "fir_tile_cf32_kernel",
+            "kernel_ms": k_ms,
+            "fp32": {"bound": "fp32_fma", "achieved": algo_fma / (k_ms * 1e-3) / 1e12, "peak": 36.2,
+                     "unit": "TFMA/s", "frac": algo_fma / (k_ms * 1e-3) / 1e12 / 36.2,
+                     "peak_source": "bin/microbench ffma, round-1 measurement"},
+            "step_kernels_ms": {"convert": prof["convert_ms"] / max(prof["convert_launches"], 1),
+                                "phase": prof["phase_ms"] / max(prof["phase_launches"], 1),
+                                "fir_tile": prof["fir_tile_ms"] / max(prof["fir_tile_launches"], 1),
+                                "fir_generic": prof["fir_generic_ms"] / max(prof["fir_generic_launches"], 1)}}
+    line = {"metric": "IQ MS/s in", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "realtime_factor": value * 1e6 / wl["fs"], "kernels_used": kinds, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": 3 * args.steps, "roofline": roof}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -282,10 +413,14 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         # rank 0 must print exactly ONE line on stdout; NCCL's version banner goes there too
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module("sdr-server_b200")
+    if wl["name"] == "cfg5":
+        rc = run_broadcast_workload(args, wl, config, rank, world, local_rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return rc
 
     def barrier():
         torch.cuda.synchronize()
