@@ -340,14 +340,14 @@ def run_broadcast_workload(args, wl, config, rank, world, local_rank):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    k_ms = prof["fir_generic_ms"] / max(prof["fir_generic_launches"], 1)
-    if prof["fir_tile_launches"] > 0:
-        k_ms = prof["fir_tile_ms"] / prof["fir_tile_launches"]
+    dom = max(("fir_tile", "fir_long", "fir_generic"), key=lambda k: prof[f"{k}_ms"])
+    k_ms = prof[f"{dom}_ms"] / max(prof[f"{dom}_launches"], 1)
     algo_bytes = nbytes + 8 * n_out_per_block / world
     algo_fma = 4.0 * prof["algo_macs"] / max(prof["blocks"], 1)
     roof = {"bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-            "kernel": "fir_generic_cf32_kernel (per rank)" if prof["fir_tile_launches"] == 0 else "fir_tile_cf32_kernel",
+            "kernel": {"fir_tile": "fir_tile_cf32_kernel", "fir_generic": "fir_generic_cf32_kernel",
+                       "fir_long": "fir_long_cf32_kernel + fir_long_reduce_kernel"}[dom] + " (per rank)",
             "kernel_ms": k_ms,
             "fp32": {"bound": "fp32_fma", "achieved": algo_fma / (k_ms * 1e-3) / 1e12, "peak": 36.2,
                      "unit": "TFMA/s", "frac": algo_fma / (k_ms * 1e-3) / 1e12 / 36.2,
@@ -355,6 +355,7 @@ def run_broadcast_workload(args, wl, config, rank, world, local_rank):
             "step_kernels_ms": {"convert": prof["convert_ms"] / max(prof["convert_launches"], 1),
                                 "phase": prof["phase_ms"] / max(prof["phase_launches"], 1),
                                 "fir_tile": prof["fir_tile_ms"] / max(prof["fir_tile_launches"], 1),
+                                "fir_long": prof["fir_long_ms"] / max(prof["fir_long_launches"], 1),
                                 "fir_generic": prof["fir_generic_ms"] / max(prof["fir_generic_launches"], 1)}}
     line = {"metric": "IQ MS/s in", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -560,8 +561,11 @@ def main():
     roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": traffic,
             "peak_source": peak_src, "kernel": "fir_tile_cf32_kernel", "algorithmic_bytes_per_launch": algo_bytes}
     fp32 = None
-    if prof["fir_tile_launches"] > 0:
-        k_ms = prof["fir_tile_ms"] / prof["fir_tile_launches"]
+    dom = max(("fir_tile", "fir_long", "fir_generic"), key=lambda k: prof[f"{k}_ms"])
+    roof["kernel"] = {"fir_tile": "fir_tile_cf32_kernel", "fir_long": "fir_long_cf32_kernel + fir_long_reduce_kernel",
+                      "fir_generic": "fir_generic_cf32_kernel"}[dom]
+    if prof[f"{dom}_launches"] > 0:
+        k_ms = prof[f"{dom}_ms"] / prof[f"{dom}_launches"]
         roof["kernel_ms"] = k_ms
         roof["achieved"] = algo_bytes / (k_ms * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / hbm_peak
@@ -589,10 +593,11 @@ def main():
     roof["step_kernels_ms"] = {"convert": prof["convert_ms"] / max(prof["convert_launches"], 1),
                                "phase": prof["phase_ms"] / max(prof["phase_launches"], 1),
                                "fir_tile": prof["fir_tile_ms"] / max(prof["fir_tile_launches"], 1),
+                               "fir_long": prof["fir_long_ms"] / max(prof["fir_long_launches"], 1),
                                "fir_generic": prof["fir_generic_ms"] / max(prof["fir_generic_launches"], 1)}
 
-    launches_per_step = sum(1 for k in ("convert", "phase", "fir_tile", "fir_generic")
-                            if prof[f"{k}_launches"] > 0)
+    launches_per_step = sum(1 for k in ("convert", "phase", "fir_tile", "fir_generic") if prof[f"{k}_launches"] > 0)
+    launches_per_step += 2 if prof["fir_long_launches"] > 0 else 0
     line = {"metric": "IQ MS/s in", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

@@ -119,6 +119,8 @@ typedef struct {
   uint64_t tile_macs;    /* complex MACs issued by the tiled kernel incl. padding */
   uint64_t algo_macs;    /* algorithmic complex MACs: sum n_out * taps_len */
   /* host side of xlg_submit (always counted, also with profiling off) */
+  double fir_long_ms;    /* split-K long-filter FIR + ordered reduction (both kernels) */
+  uint64_t fir_long_launches;
   double host_submit_ms; /* wall time spent inside xlg_submit, including ...          */
   double host_wait_ms;   /* ... the part spent waiting for a free slot (GPU is behind) */
   uint64_t submits;
@@ -127,7 +129,7 @@ int xlg_profile_enable(xlg_group *g, int on);
 int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset);
 
 /* Introspection for tests: history length (src/xlating.c:29 history_offset) and
- * which kernel currently serves the client (0 = generic, 1 = tiled). */
+ * which kernel currently serves the client (0 = generic, 1 = tiled, 2 = long-filter split-K). */
 int xlg_client_info(const xlg_group *g, int client_id, size_t *history, int *kernel_kind);
 
 #ifdef __cplusplus

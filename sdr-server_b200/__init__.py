@@ -58,6 +58,7 @@ class XlgProfile(C.Structure):
                 ("fir_generic_launches", C.c_uint64), ("phase_launches", C.c_uint64),
                 ("convert_launches", C.c_uint64), ("blocks", C.c_uint64), ("out_samples", C.c_uint64),
                 ("in_samples", C.c_uint64), ("tile_macs", C.c_uint64), ("algo_macs", C.c_uint64),
+                ("fir_long_ms", C.c_double), ("fir_long_launches", C.c_uint64),
                 ("host_submit_ms", C.c_double), ("host_wait_ms", C.c_double), ("submits", C.c_uint64)]
 
 

@@ -88,12 +88,13 @@ struct Slot {
   float2 *d_out = nullptr;
   short2 *d_qout = nullptr;
   float2 *d_phases = nullptr;
+  float2 *d_partial = nullptr;  // split-K partial sums of the long-filter classes
   short2 *d_qphases = nullptr;
   BlkInfo *d_blk = nullptr;
   size_t blk_cap = 0;
   cudaEvent_t ev_h2d = nullptr, ev_conv = nullptr, ev_phase = nullptr, ev_fir = nullptr, ev_done = nullptr;
-  cudaEvent_t pf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool pf_conv = false, pf_phase = false, pf_tile = false, pf_gen = false;
+  cudaEvent_t pf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pf_conv = false, pf_phase = false, pf_tile = false, pf_gen = false, pf_long = false;
   std::atomic<int64_t> ticket{-1};
   bool q15 = false;
   bool harvested = true;
@@ -188,6 +189,8 @@ struct xlg_group {
   bool q_alloc = false;
 
   std::vector<TileClassHost> classes;
+  std::vector<TileClassHost> long_classes;  // split-K long-filter classes (fir_long_cf32_kernel)
+  size_t partial_cap = 0;                   // float2 per slot partial-sum buffer
   int n_generic = 0;
   int max_client = 0;     // highest active id + 1
   bool dirty = true;
@@ -225,12 +228,14 @@ static void slot_free(Slot &s) {
   if (s.d_out) cudaFree(s.d_out);
   if (s.d_qout) cudaFree(s.d_qout);
   if (s.d_phases) cudaFree(s.d_phases);
+  if (s.d_partial) cudaFree(s.d_partial);
   if (s.d_qphases) cudaFree(s.d_qphases);
   if (s.d_blk) cudaFree(s.d_blk);
   s.d_raw = s.h_raw = nullptr;
   s.d_out = nullptr;
   s.d_qout = nullptr;
   s.d_phases = nullptr;
+  s.d_partial = nullptr;
   s.d_qphases = nullptr;
   s.d_blk = nullptr;
 }
@@ -264,6 +269,10 @@ static void harvest_locked(xlg_group *g, Slot &s) {
   if (s.pf_gen && cudaEventElapsedTime(&ms, s.pf[6], s.pf[7]) == cudaSuccess) {
     g->prof.fir_generic_ms += ms;
     g->prof.fir_generic_launches++;
+  }
+  if (s.pf_long && cudaEventElapsedTime(&ms, s.pf[8], s.pf[9]) == cudaSuccess) {
+    g->prof.fir_long_ms += ms;
+    g->prof.fir_long_launches++;
   }
   g->prof.blocks++;
   g->prof.out_samples += s.out_samples;
@@ -425,6 +434,7 @@ static int rebuild_layout(xlg_group *g) {
   //    zero-history window (zero_before behind the next window start, or the
   //    stream origin where the ring itself is still zero)
   g->classes.clear();
+  g->long_classes.clear();
   g->n_generic = 0;
   std::map<std::tuple<uint32_t, size_t, long long>, std::vector<int>> buckets;
   for (int i = 0; i < nc; i++) {
@@ -455,8 +465,11 @@ static int rebuild_layout(xlg_group *g) {
     const int xs_len = (KT - 1) * Dp + L;
     const size_t smem = smem_fixed + ((size_t)xs_len + 8) * sizeof(float2);
     const size_t typical_out = g->max_input_len / 2 / D;
-    if (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs ||
-        (int)g->classes.size() >= T_MAX_CLASSES) {
+    // too long for a shared-memory tile -> split-K long-filter class (natural layout)
+    const bool as_long = smem > (size_t)kTileMaxSmem && typical_out >= 1 &&
+                         (int)g->long_classes.size() < T_MAX_CLASSES && !getenv("XLATING_B200_NO_LONG");
+    if (!as_long && (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs ||
+                     (int)g->classes.size() >= T_MAX_CLASSES)) {
       // stays on the generic kernel for good: do not re-derive the layout every block
       for (int id : ids) g->clients[id].tile_ineligible = true;
       continue;
@@ -466,17 +479,19 @@ static int rebuild_layout(xlg_group *g) {
     ch.T = T;
     ch.members = ids;
     ch.k.D = (int)D;
-    ch.k.Dp = Dp;
-    ch.k.L = L;
+    ch.k.Dp = as_long ? (int)D : Dp;
+    ch.k.L = as_long ? (int)((T + 7) / 8 * 8) : L;
     ch.k.xs_len = xs_len;
     ch.k.n_groups = (int)((ids.size() + T_CG - 1) / T_CG);
     ch.k.n_members = (int)ids.size();
-    ch.k.natural = natural ? 1 : 0;
+    ch.k.natural = (natural || as_long) ? 1 : 0;
+    ch.k.nseg = as_long ? (ch.k.L + W_JS - 1) / W_JS : 0;
+    const int Lp = ch.k.L, Dpp = ch.k.Dp;
     ch.k.members_off = (int)members.size();
     ch.k.taps_off = (long long)tile_taps.size();
     for (int gi = 0; gi < ch.k.n_groups; gi++) {
       const size_t base = tile_taps.size();
-      tile_taps.resize(base + (size_t)L * T_CG, make_float2(0.f, 0.f));
+      tile_taps.resize(base + (size_t)Lp * T_CG, make_float2(0.f, 0.f));
       for (int m = 0; m < T_CG; m++) {
         const size_t idx = (size_t)gi * T_CG + m;
         if (idx >= ids.size()) {
@@ -487,15 +502,18 @@ static int rebuild_layout(xlg_group *g) {
         const int id = ids[idx];
         members.push_back(g->clients[id].out_off);  // the kernel only needs the output row
         member_incr.push_back(make_float2(g->clients[id].incr_re, g->clients[id].incr_im));
-        g->clients[id].kind = 1;
+        g->clients[id].kind = as_long ? 2 : 1;
         const HostClient &h = g->clients[id];
         for (size_t j = 0; j < T; j++) {
-          const size_t f = (j / D) * Dp + (j % D);
+          const size_t f = (j / D) * Dpp + (j % D);
           tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
         }
       }
     }
-    g->classes.push_back(ch);
+    if (as_long)
+      g->long_classes.push_back(ch);
+    else
+      g->classes.push_back(ch);
   }
   // heaviest classes first: their CTAs are scheduled first and the lighter ones
   // fill the tail of the launch
@@ -523,7 +541,11 @@ static int rebuild_layout(xlg_group *g) {
   {
     std::vector<int> order;
     size_t table = 0;
-    for (TileClassHost &ch : g->classes) {
+    std::vector<TileClassHost *> tabled;
+    for (TileClassHost &ch : g->classes) tabled.push_back(&ch);
+    for (TileClassHost &ch : g->long_classes) tabled.push_back(&ch);
+    for (TileClassHost *chp : tabled) {
+      TileClassHost &ch = *chp;
       int cap = 0;
       for (int id : ch.members) cap = std::max(cap, g->clients[id].out_cap);
       cap = cap / 2 + 1;  // only even outputs are tabulated
@@ -565,6 +587,25 @@ static int rebuild_layout(xlg_group *g) {
     if (!order.empty()) {
       CU_OK(cudaMalloc(&g->d_order, order.size() * sizeof(int)));
       CU_OK(cudaMemcpy(g->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    {
+      size_t part = 0;
+      for (TileClassHost &ch : g->long_classes) {
+        int cap = 0;
+        for (int id : ch.members) cap = std::max(cap, g->clients[id].out_cap);
+        const size_t kpad_max = ((size_t)cap + W_KT - 1) / W_KT * W_KT;
+        ch.k.part_off = (long long)part;
+        ch.k.kpad = (int)kpad_max;
+        part += (size_t)ch.k.nseg * ch.k.n_groups * kpad_max * T_CG;
+      }
+      if (part > g->partial_cap) {
+        g->partial_cap = part;
+        for (Slot &sl : g->slots) {
+          if (sl.d_partial) cudaFree(sl.d_partial);
+          sl.d_partial = nullptr;
+          CU_OK(cudaMalloc(&sl.d_partial, g->partial_cap * sizeof(float2)));
+        }
+      }
     }
     if (table > g->phase_cap) {
       g->phase_cap = table + table / 4 + 1024;
@@ -738,7 +779,7 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     cudaEvent_t *evs[] = {&s.ev_h2d, &s.ev_conv, &s.ev_phase, &s.ev_fir, &s.ev_done};
     for (cudaEvent_t *ev : evs)
       if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return fail(-EIO);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
       if (cudaEventCreate(&s.pf[i]) != cudaSuccess) return fail(-EIO);
   }
   if (cudaEventCreate(&g->ev_t0) != cudaSuccess || cudaEventCreate(&g->ev_t1) != cudaSuccess) return fail(-EIO);
@@ -755,7 +796,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
       cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
       cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
-          cudaSuccess) {
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
@@ -810,7 +852,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
     cudaEvent_t evs[] = {s.ev_h2d, s.ev_conv, s.ev_phase, s.ev_fir, s.ev_done};
     for (cudaEvent_t ev : evs)
       if (ev) cudaEventDestroy(ev);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
       if (s.pf[i]) cudaEventDestroy(s.pf[i]);
   }
   for (HostOut &h : g->ring_out) {
@@ -1141,6 +1183,40 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
 #undef XL_LAUNCH_TILE
       if (g->d_trace != nullptr) g->trace_ctas = std::min(ctas, 16384);
       if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], cs));
+    }
+  }
+  // ---- long filters: split-K partial sums, then the ordered reduction ----
+  s.pf_long = false;
+  if (!q15 && !g->long_classes.empty()) {
+    TileLaunch P;
+    memset(&P, 0, sizeof(P));
+    int ctas = 0, max_out = 0, max_groups = 0;
+    for (TileClassHost &ch : g->long_classes) {
+      const HostClient &h0 = g->clients[ch.members[0]];
+      const int n_out = ho.n_out[ch.members[0]];
+      if (n_out <= 0) continue;
+      TileClass k = ch.k;
+      k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
+      k.n_out = n_out;
+      k.tiles = (n_out + W_KT - 1) / W_KT;
+      k.cta_begin = ctas;
+      ctas += k.nseg * k.tiles * k.n_groups;
+      max_out = std::max(max_out, n_out);
+      max_groups = std::max(max_groups, k.n_groups);
+      P.cls[P.n_classes++] = k;
+      s.tile_macs += (uint64_t)k.tiles * W_KT * (uint64_t)k.L * (uint64_t)ch.members.size();
+    }
+    if (ctas > 0) {
+      if (g->profiling) {
+        CU_OK(cudaEventRecord(s.pf[8], cs));
+        s.pf_long = true;
+      }
+      fir_long_cf32_kernel<<<ctas, W_THREADS, W_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
+                                                           s.d_partial);
+      dim3 rgrid((max_out + 7) / 8, max_groups, P.n_classes);
+      fir_long_reduce_kernel<<<rgrid, 256, 0, cs>>>(P, s.d_partial, g->d_members, g->d_member_incr, s.d_phases,
+                                                    s.d_out);
+      if (g->profiling) CU_OK(cudaEventRecord(s.pf[9], cs));
     }
   }
   if (nc > 0 && max_generic_out > 0) {

@@ -377,6 +377,7 @@ constexpr int T_CHUNK_F2 = T_JC * T_CG;       // float2 per chunk (1024)
 constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
 constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
 constexpr int T_MAX_CLASSES = 8;
+constexpr int T_RK_LONG = 4;         // outputs per thread in the long-filter kernel
 
 // Shape of the tile a CTA computes.  LO = number of output lanes in a warp, RK =
 // outputs per thread; the thread tile is RK outputs x 8 clients, the CTA tile
@@ -418,6 +419,10 @@ struct TileClass {
   int n_members;       // real clients in the class (the last group may be partly padding)
   int natural;         // 1: Dp == D, the input tile is ONE contiguous TMA bulk copy (see kernel)
   long long ph_base;   // float2 offset of (group 0, output 0, lane 0) in the oscillator table
+  // long-filter (split-K) classes only:
+  long long part_off;  // float2 offset of this class in the partial-sum buffer
+  int nseg;            // tap segments of W_JS flat taps
+  int kpad;            // outputs rounded up to the tile size (row count of the partial buffer)
 };
 
 struct TileLaunch {
@@ -688,6 +693,171 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     t[2] = (tr2 & 0x0000ffffffffffffll) | ((long long)smid << 48);  // smid in the top 16 bits
     t[3] = clock64();
   }
+}
+
+// ---------------------------------------------------------------------------
+// long filters: split-K FIR + ordered reduction
+//
+// BASELINE configs[4] (61.44 Msps -> 48 ksps) gives D = 1280 and T = 15419 taps with
+// only ~52 outputs per 256 KiB block: the window of ONE output (123 KB of cf32) does
+// not fit the tiled kernel's shared-memory tile, and (outputs x clients) alone is far
+// too little parallelism for 148 SMs.  So the tap range is cut into segments of W_JS
+// taps and every (segment, client group, output tile) is a CTA:
+//   * the x "strips" of the tile's 64 outputs for this segment (64 x W_JS samples, each
+//     strip contiguous in the ring) arrive by one TMA bulk copy per output row when
+//     the strips are 16-byte aligned (even D and window start), else by 8-byte
+//     cp.async; the segment's taps (W_JS x 32 clients, 32 KiB) by one TMA bulk copy;
+//   * the same 4-output x 8-client register tile and lane mapping (16 output lanes x
+//     2 client halves) as the tiled kernel accumulates the segment;
+//   * partial sums go to [segment][group][output][32 clients] (coalesced);
+// fir_long_reduce_kernel then adds the segments IN ORDER (deterministic), derotates
+// with the oscillator table and stores.  Same arithmetic as the other kernels up to
+// the order of the fp32 additions.
+// ---------------------------------------------------------------------------
+constexpr int W_JS = 128;             // taps per segment
+constexpr int W_KT = 64;              // outputs per CTA (16 lanes x 4)
+constexpr int W_THREADS = 64;
+constexpr int W_JSP = W_JS + 2;       // strip pitch: 16-byte aligned rows, 2-way conflicts at most
+constexpr int W_SMEM = W_JS * T_CG * 8 + 64 + W_KT * W_JSP * 8;  // 32 KiB taps + barrier + 65 KiB strips
+
+__global__ void __launch_bounds__(W_THREADS, 2)
+fir_long_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
+                     const float2 *__restrict__ tile_taps, float2 *__restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2 *ts = reinterpret_cast<float2 *>(smem);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + W_JS * T_CG * 8);
+  float2 *xs = reinterpret_cast<float2 *>(smem + W_JS * T_CG * 8 + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o = lane & 15, h = lane >> 4;
+  const int cbase = warp * 16 + h * T_RC;
+
+  int ci = 0;
+  while (ci + 1 < P.n_classes && (int)blockIdx.x >= P.cls[ci + 1].cta_begin) ci++;
+  const TileClass &K = P.cls[ci];
+  const int local = (int)blockIdx.x - K.cta_begin;
+  const int seg = local % K.nseg;
+  const int rest = local / K.nseg;
+  const int tile = rest % K.tiles;
+  const int grp = rest / K.tiles;
+  const int k0 = tile * W_KT;
+  const int f0 = seg * W_JS;
+  const int len = min(W_JS, K.L - f0);  // multiple of 8
+  const int D = K.D;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long w0 = K.first + (long long)k0 * D + f0;  // first sample of strip 0
+  const bool aligned = ((K.first | (long long)D) & 1) == 0;  // f0 and k0*D are even then
+  const unsigned strip_bytes = (unsigned)len * 8u;
+  if (tid == 0) {
+    const unsigned tap_bytes = (unsigned)len * T_CG * 8u;
+    mbar_expect_tx(bar, tap_bytes + (aligned ? W_KT * strip_bytes : 0u));
+    tma_bulk_g2s(ts, tile_taps + K.taps_off + ((long long)grp * K.L + f0) * T_CG, tap_bytes, bar);
+  }
+  __syncthreads();  // expect_tx is posted before any strip copy can complete
+  if (aligned) {
+    // one strip per thread: x[(k0 + tid)*D + f0 .. + len), contiguous in the ring
+    const unsigned idx = (unsigned)((unsigned long long)(w0 + (long long)tid * D)) & mask;
+    const unsigned n1 = min((unsigned)len, mask + 1u - idx);
+    tma_bulk_g2s(xs + tid * W_JSP, ring + idx, n1 * 8u, bar);
+    if (n1 < (unsigned)len) tma_bulk_g2s(xs + tid * W_JSP + n1, ring, ((unsigned)len - n1) * 8u, bar);
+  } else {
+    for (int e = tid; e < W_KT * W_JS; e += W_THREADS) {
+      const int k = e / W_JS, f = e - k * W_JS;
+      if (f < len) {
+        const long long ab = w0 + (long long)k * D + f;
+        cp_async_8(xs + k * W_JSP + f, ring + ((unsigned)((unsigned long long)ab) & mask));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  mbar_wait(bar, 0);
+
+  float2 acc[T_RK_LONG][T_RC];
+#pragma unroll
+  for (int i = 0; i < T_RK_LONG; i++)
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+  const float2 *xb[T_RK_LONG];
+#pragma unroll
+  for (int i = 0; i < T_RK_LONG; i++) xb[i] = xs + (o + 16 * i) * W_JSP;
+  const float4 *tp = reinterpret_cast<const float4 *>(ts + cbase);
+
+  const bool warp_active = grp * T_CG + warp * 16 < K.n_members;
+  if (warp_active) {
+#pragma unroll 1
+    for (int f = 0; f < len; f += T_UNROLL) {
+#pragma unroll
+      for (int u = 0; u < T_UNROLL; u++) {
+        float2 x[T_RK_LONG];
+        float4 tq[T_RC / 2];
+#pragma unroll
+        for (int i = 0; i < T_RK_LONG; i++) x[i] = xb[i][f + u];
+#pragma unroll
+        for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+        for (int i = 0; i < T_RK_LONG; i++) {
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) {
+            float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+            a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+            a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+            a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+            a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+            a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+            a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+            a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+            a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+          }
+        }
+      }
+    }
+    // partial sums: [segment][group][output][32 clients]
+    float2 *pp = partial + K.part_off + (((long long)seg * K.n_groups + grp) * K.kpad + k0) * T_CG + cbase;
+#pragma unroll
+    for (int i = 0; i < T_RK_LONG; i++) {
+      float4 *row = reinterpret_cast<float4 *>(pp + (size_t)(o + 16 * i) * T_CG);
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++)
+        row[q] = make_float4(acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y);
+    }
+  }
+}
+
+// Adds the segments in order, derotates, stores.  Block = 32 clients (lanes) x 8 outputs.
+__global__ void __launch_bounds__(256)
+fir_long_reduce_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ partial,
+                       const int *__restrict__ member_off, const float2 *__restrict__ member_incr,
+                       const float2 *__restrict__ phases, float2 *__restrict__ out) {
+  const int ci = blockIdx.z;
+  if (ci >= P.n_classes) return;
+  const TileClass &K = P.cls[ci];
+  const int grp = blockIdx.y;
+  if (grp >= K.n_groups) return;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= K.n_out) return;
+  const int off = __ldg(member_off + K.members_off + grp * T_CG + lane);
+  if (off < 0) return;
+  const float2 *pp = partial + K.part_off + ((long long)grp * K.kpad + k) * T_CG + lane;
+  const size_t seg_stride = (size_t)K.n_groups * K.kpad * T_CG;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int s = 0; s < K.nseg; s++) {
+    const float2 v = pp[(size_t)s * seg_stride];
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  float2 ph = phases[K.ph_base + (long long)grp * K.ph_stride + (size_t)(k >> 1) * 32 + lane];
+  if (k & 1) ph = cmul_unfused(ph, __ldg(member_incr + K.members_off + grp * T_CG + lane));
+  out[off + k] = cmul_unfused(acc, ph);  // src/xlating.c:70
 }
 
 }  // namespace xl

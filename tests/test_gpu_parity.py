@@ -353,6 +353,43 @@ def test_group_very_long_filter_config5_shape(pkg):
     g.close()
 
 
+def test_group_long_filter_split_k_kernel(pkg):
+    """>= 8 aligned clients with a filter too long for a shared-memory tile use the
+    split-K long-filter kernel (kernel kind 2): config-5 shape (aligned TMA strips) and an
+    odd-decimation case (cp.async strips, many output tiles)."""
+    rng = np.random.default_rng(67)
+    # (a) BASELINE configs[4] shape
+    fs, max_in = 61440000, 131072
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 9600)
+    g = pkg.Group(fs, max_in)
+    centers = [int(-30000000 + c * 4100000) for c in range(12)]
+    ids = [g.add_client(1280, taps, c) for c in centers]
+    oracles = [po.OracleFilter(1280, taps, c, fs, max_in) for c in centers]
+    for blk, n in enumerate([max_in, max_in, 50000, max_in]):
+        x = rand_block(rng, "cs16", n)
+        t = g.submit("cs16", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cs16", x), f"(a) blk {blk} c{cid}")
+    assert {g.client_info(c)[1] for c in ids} == {2}
+    g.close()
+    # (b) odd decimation, 24001 taps, 1638 outputs per block (26 output tiles, unaligned strips)
+    fs, max_in, D, T = 1000000, 16384, 5, 24001
+    taps = (rng.standard_normal(T) * 0.01).astype(np.float32)
+    g = pkg.Group(fs, max_in)
+    centers = [int(-400000 + c * 90000) for c in range(9)]
+    ids = [g.add_client(D, taps, c) for c in centers]
+    oracles = [po.OracleFilter(D, taps, c, fs, max_in) for c in centers]
+    for blk in range(2):
+        x = rand_block(rng, "cu8", max_in)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"(b) blk {blk} c{cid}")
+    assert {g.client_info(c)[1] for c in ids} == {2}
+    g.close()
+
+
 def test_group_rejects_oversized_block(pkg, capfd):
     """the reference overflows its work buffer here (src/xlating.c:353); we refuse"""
     g = pkg.Group(48000, 1000)
