@@ -850,7 +850,20 @@ fir_long_reduce_kernel(const __grid_constant__ TileLaunch P, const float2 *__res
   const float2 *pp = partial + K.part_off + ((long long)grp * K.kpad + k) * T_CG + lane;
   const size_t seg_stride = (size_t)K.n_groups * K.kpad * T_CG;
   float2 acc = make_float2(0.f, 0.f);
-  for (int s = 0; s < K.nseg; s++) {
+  // loads in batches of 8 (independent, so their L2 latencies overlap); the additions
+  // stay strictly in segment order
+  int s = 0;
+  for (; s + 8 <= K.nseg; s += 8) {
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = pp[(size_t)(s + u) * seg_stride];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+    }
+  }
+  for (; s < K.nseg; s++) {
     const float2 v = pp[(size_t)s * seg_stride];
     acc.x += v.x;
     acc.y += v.y;
