@@ -81,6 +81,7 @@ struct HostClient {
   int taps_off = 0;
   int ph_off = 0;
   bool tile_ineligible = false;  // its class cannot use the tiled kernel (shared memory, too few outputs)
+  bool pending_settle = false;   // still inside its zero-history window at the last layout rebuild
 };
 
 struct Slot {
@@ -152,8 +153,10 @@ struct HostOut {
 
 struct TileClassHost {
   TileClass k;
-  std::vector<int> members;
+  std::vector<int> members;  // client id per member slot, -1 = padding; 32 slots per group
+  std::vector<int> real;     // the real client ids
   size_t T;
+  bool merged = false;       // members may have different window alignments (natural layout only)
 };
 
 }  // namespace
@@ -181,6 +184,7 @@ struct xlg_group {
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
   int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
+  int *d_member_cid = nullptr;      // client id per member slot (-1 = padding)
   float2 *d_member_incr = nullptr;  // oscillator step per member slot (same indexing as d_members)
   int *d_order = nullptr;   // clients in oscillator-table order, 32 per group, -1 = padding
   int n_order = 0;
@@ -430,90 +434,134 @@ static int rebuild_layout(xlg_group *g) {
   CU_OK(cudaMemcpy(g->d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(g->d_qtaps, qtaps.data(), qtaps.size() * sizeof(short2), cudaMemcpyHostToDevice));
 
-  // 3. classes for the tiled kernel: identical (D, T, hist) and no pending
-  //    zero-history window (zero_before behind the next window start, or the
-  //    stream origin where the ring itself is still zero)
+  // 3. classes for the tiled / long-filter kernels.  A class is a set of clients with
+  //    the same (D, T) whose zero-history window has passed (zero_before behind the
+  //    next window start, or the stream origin where the ring itself is still zero).
+  //    With the natural input layout the members may have different window alignments
+  //    (they attached at different stream positions): the kernel shifts each 8-client
+  //    subgroup by its own delta, so members are packed into subgroups of 8 with equal
+  //    alignment.  The skewed layout and the long-filter kernel need identical
+  //    alignment (hist) across the class.
   g->classes.clear();
   g->long_classes.clear();
   g->n_generic = 0;
+  const int KT = 64;  // largest production tile shape: decides eligibility (smaller shapes need less)
+  const size_t smem_fixed = (size_t)T_SMEM_FIXED;
+  struct Mode {
+    bool natural, as_long, eligible;
+    int Dp, L;
+  };
+  auto mode_of = [&](uint32_t D, size_t T) {
+    Mode m;
+    const unsigned g16 = (D % 16 == 0) ? 16u : (D % 8 == 0) ? 8u : (D % 4 == 0) ? 4u : (D % 2 == 0) ? 2u : 1u;
+    m.natural = g16 <= 2 && !getenv("XLATING_B200_SKEWED");
+    m.Dp = m.natural ? (int)D : (int)(D | 1u);
+    const size_t q_last = (T - 1) / D, r_last = (T - 1) % D;
+    m.L = (int)(((q_last * m.Dp + r_last + 1) + 7) / 8 * 8);
+    const size_t smem = smem_fixed + ((size_t)(KT - 1) * m.Dp + m.L + D + 10) * sizeof(float2);
+    const size_t typical_out = g->max_input_len / 2 / D;
+    // too long for a shared-memory tile -> split-K long-filter class (natural layout)
+    m.as_long = smem > (size_t)kTileMaxSmem && typical_out >= 1 && !getenv("XLATING_B200_NO_LONG");
+    m.eligible = m.as_long || (smem <= (size_t)kTileMaxSmem && typical_out >= (size_t)kTileMinOutputs);
+    if (m.as_long) {
+      m.natural = true;
+      m.Dp = (int)D;
+      m.L = (int)((T + 7) / 8 * 8);
+    }
+    return m;
+  };
   std::map<std::tuple<uint32_t, size_t, long long>, std::vector<int>> buckets;
   for (int i = 0; i < nc; i++) {
     HostClient &h = g->clients[i];
     if (!h.active) continue;
     h.kind = 0;
+    h.tile_ineligible = false;
+    h.pending_settle = false;
     const long long first = g->S - h.hist;
     const bool settled = (h.zero_before == 0 && g->S < (long long)g->ring_cap / 2) || h.zero_before <= first;
-    h.tile_ineligible = false;
-    if (!(g->flags & XLG_FORCE_GENERIC) && settled) buckets[std::make_tuple(h.D, h.T, h.hist)].push_back(i);
+    if (g->flags & XLG_FORCE_GENERIC) continue;
+    const Mode m = mode_of(h.D, h.T);
+    if (!m.eligible) {
+      h.tile_ineligible = true;
+      continue;
+    }
+    if (!settled) {
+      h.pending_settle = true;  // re-derive the layout once its window has passed
+      continue;
+    }
+    const bool merge = m.natural && !m.as_long && !getenv("XLATING_B200_NO_MERGE");
+    buckets[std::make_tuple(h.D, h.T, merge ? -1ll : h.hist)].push_back(i);
   }
-  std::vector<int> members;
+  std::vector<int> members;       // output row offset per member slot
+  std::vector<int> member_cid;    // client id per member slot
   std::vector<float2> member_incr;
-  std::vector<float2> tile_taps;  // v1: one float2 per client-tap; v2: two (tr,tr),(ti,ti)
-  const int KT = 64;  // largest production tile shape: decides eligibility (smaller shapes need less)
-  const size_t smem_fixed = (size_t)T_SMEM_FIXED;
+  std::vector<float2> tile_taps;
   for (auto &kv : buckets) {
     const uint32_t D = std::get<0>(kv.first);
     const size_t T = std::get<1>(kv.first);
-    std::vector<int> &ids = kv.second;
-    if ((int)ids.size() < kTileMinClients) continue;
-    // natural layout when the lane stride D is at most 2-way bank conflicting
-    const unsigned g16 = (D % 16 == 0) ? 16u : (D % 8 == 0) ? 8u : (D % 4 == 0) ? 4u : (D % 2 == 0) ? 2u : 1u;
-    const bool natural = g16 <= 2 && !getenv("XLATING_B200_SKEWED");
-    const int Dp = natural ? (int)D : (int)(D | 1u);
-    const size_t q_last = (T - 1) / D, r_last = (T - 1) % D;
-    const int L = (int)(((q_last * Dp + r_last + 1) + 7) / 8 * 8);
-    const int xs_len = (KT - 1) * Dp + L;
-    const size_t smem = smem_fixed + ((size_t)xs_len + 8) * sizeof(float2);
-    const size_t typical_out = g->max_input_len / 2 / D;
-    // too long for a shared-memory tile -> split-K long-filter class (natural layout)
-    const bool as_long = smem > (size_t)kTileMaxSmem && typical_out >= 1 &&
-                         (int)g->long_classes.size() < T_MAX_CLASSES && !getenv("XLATING_B200_NO_LONG");
-    if (!as_long && (smem > (size_t)kTileMaxSmem || typical_out < (size_t)kTileMinOutputs ||
-                     (int)g->classes.size() >= T_MAX_CLASSES)) {
-      // stays on the generic kernel for good: do not re-derive the layout every block
-      for (int id : ids) g->clients[id].tile_ineligible = true;
+    const bool merged = std::get<2>(kv.first) < 0;
+    const Mode m = mode_of(D, T);
+    // subgroups of 8 slots with one window alignment each
+    std::map<long long, std::vector<int>> by_align;
+    for (int id : kv.second) by_align[merged ? (long long)(T - 1) - g->clients[id].hist : 0].push_back(id);
+    std::vector<int> slots;
+    std::vector<int> real;
+    for (auto &al : by_align) {
+      if (merged && al.second.size() < 2) {
+        // a lone alignment would occupy an 8-slot subgroup by itself: generic kernel
+        g->clients[al.second[0]].tile_ineligible = true;
+        continue;
+      }
+      for (size_t i = 0; i < al.second.size(); i++) {
+        slots.push_back(al.second[i]);
+        real.push_back(al.second[i]);
+      }
+      while (slots.size() % T_RC != 0) slots.push_back(-1);
+    }
+    std::vector<TileClassHost> &dest = m.as_long ? g->long_classes : g->classes;
+    if ((int)real.size() < kTileMinClients || (int)dest.size() >= T_MAX_CLASSES) {
+      if ((int)dest.size() >= T_MAX_CLASSES)
+        for (int id : real) g->clients[id].tile_ineligible = true;
       continue;
     }
+    while (slots.size() % T_CG != 0) slots.push_back(-1);
     TileClassHost ch;
     memset(&ch.k, 0, sizeof(ch.k));
     ch.T = T;
-    ch.members = ids;
+    ch.members = slots;
+    ch.real = real;
+    ch.merged = merged;
     ch.k.D = (int)D;
-    ch.k.Dp = as_long ? (int)D : Dp;
-    ch.k.L = as_long ? (int)((T + 7) / 8 * 8) : L;
-    ch.k.xs_len = xs_len;
-    ch.k.n_groups = (int)((ids.size() + T_CG - 1) / T_CG);
-    ch.k.n_members = (int)ids.size();
-    ch.k.natural = (natural || as_long) ? 1 : 0;
-    ch.k.nseg = as_long ? (ch.k.L + W_JS - 1) / W_JS : 0;
-    const int Lp = ch.k.L, Dpp = ch.k.Dp;
+    ch.k.Dp = m.Dp;
+    ch.k.L = m.L;
+    ch.k.n_groups = (int)(slots.size() / T_CG);
+    ch.k.n_members = (int)real.size();
+    ch.k.natural = m.natural ? 1 : 0;
+    ch.k.nseg = m.as_long ? (ch.k.L + W_JS - 1) / W_JS : 0;
     ch.k.members_off = (int)members.size();
     ch.k.taps_off = (long long)tile_taps.size();
-    for (int gi = 0; gi < ch.k.n_groups; gi++) {
-      const size_t base = tile_taps.size();
-      tile_taps.resize(base + (size_t)Lp * T_CG, make_float2(0.f, 0.f));
-      for (int m = 0; m < T_CG; m++) {
-        const size_t idx = (size_t)gi * T_CG + m;
-        if (idx >= ids.size()) {
-          members.push_back(-1);
-          member_incr.push_back(make_float2(1.f, 0.f));
-          continue;
-        }
-        const int id = ids[idx];
-        members.push_back(g->clients[id].out_off);  // the kernel only needs the output row
-        member_incr.push_back(make_float2(g->clients[id].incr_re, g->clients[id].incr_im));
-        g->clients[id].kind = as_long ? 2 : 1;
-        const HostClient &h = g->clients[id];
-        for (size_t j = 0; j < T; j++) {
-          const size_t f = (j / D) * Dpp + (j % D);
-          tile_taps[base + f * T_CG + m] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
-        }
+    const size_t base = tile_taps.size();
+    tile_taps.resize(base + slots.size() * (size_t)m.L, make_float2(0.f, 0.f));
+    for (size_t sl = 0; sl < slots.size(); sl++) {
+      const int id = slots[sl];
+      member_cid.push_back(id);
+      if (id < 0) {
+        members.push_back(-1);
+        member_incr.push_back(make_float2(1.f, 0.f));
+        continue;
+      }
+      HostClient &h = g->clients[id];
+      members.push_back(h.out_off);
+      member_incr.push_back(make_float2(h.incr_re, h.incr_im));
+      h.kind = m.as_long ? 2 : 1;
+      const size_t gi = sl / T_CG, mslot = sl % T_CG;
+      float2 *dst = tile_taps.data() + base + gi * (size_t)m.L * T_CG;
+      for (size_t j = 0; j < T; j++) {
+        const size_t f = (j / D) * m.Dp + (j % D);
+        dst[f * T_CG + mslot] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
       }
     }
-    if (as_long)
-      g->long_classes.push_back(ch);
-    else
-      g->classes.push_back(ch);
+    dest.push_back(ch);
   }
   // heaviest classes first: their CTAs are scheduled first and the lighter ones
   // fill the tail of the launch
@@ -523,14 +571,18 @@ static int rebuild_layout(xlg_group *g) {
   if (g->d_tile_taps) cudaFree(g->d_tile_taps);
   if (g->d_members) cudaFree(g->d_members);
   if (g->d_member_incr) cudaFree(g->d_member_incr);
+  if (g->d_member_cid) cudaFree(g->d_member_cid);
   g->d_tile_taps = nullptr;
   g->d_members = nullptr;
   g->d_member_incr = nullptr;
+  g->d_member_cid = nullptr;
   if (!tile_taps.empty()) {
     CU_OK(cudaMalloc(&g->d_tile_taps, tile_taps.size() * sizeof(float2)));
     CU_OK(cudaMemcpy(g->d_tile_taps, tile_taps.data(), tile_taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
     CU_OK(cudaMalloc(&g->d_members, members.size() * sizeof(int)));
     CU_OK(cudaMemcpy(g->d_members, members.data(), members.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU_OK(cudaMalloc(&g->d_member_cid, member_cid.size() * sizeof(int)));
+    CU_OK(cudaMemcpy(g->d_member_cid, member_cid.data(), member_cid.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU_OK(cudaMalloc(&g->d_member_incr, member_incr.size() * sizeof(float2)));
     CU_OK(cudaMemcpy(g->d_member_incr, member_incr.data(), member_incr.size() * sizeof(float2),
                      cudaMemcpyHostToDevice));
@@ -547,14 +599,14 @@ static int rebuild_layout(xlg_group *g) {
     for (TileClassHost *chp : tabled) {
       TileClassHost &ch = *chp;
       int cap = 0;
-      for (int id : ch.members) cap = std::max(cap, g->clients[id].out_cap);
+      for (int id : ch.real) cap = std::max(cap, g->clients[id].out_cap);
       cap = cap / 2 + 1;  // only even outputs are tabulated
       ch.k.ph_base = (long long)table;
       ch.k.ph_stride = cap * 32;
       for (int gi = 0; gi < ch.k.n_groups; gi++) {
         for (int m = 0; m < T_CG; m++) {
           const size_t idx = (size_t)gi * T_CG + m;
-          if (idx < ch.members.size()) {
+          if (idx < ch.members.size() && ch.members[idx] >= 0) {
             g->clients[ch.members[idx]].ph_off = (int)(table + m);
             order.push_back(ch.members[idx]);
           } else {
@@ -592,7 +644,7 @@ static int rebuild_layout(xlg_group *g) {
       size_t part = 0;
       for (TileClassHost &ch : g->long_classes) {
         int cap = 0;
-        for (int id : ch.members) cap = std::max(cap, g->clients[id].out_cap);
+        for (int id : ch.real) cap = std::max(cap, g->clients[id].out_cap);
         const size_t kpad_max = ((size_t)cap + W_KT - 1) / W_KT * W_KT;
         ch.k.part_off = (long long)part;
         ch.k.kpad = (int)kpad_max;
@@ -870,6 +922,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_tile_taps) cudaFree(g->d_tile_taps);
   if (g->d_members) cudaFree(g->d_members);
   if (g->d_member_incr) cudaFree(g->d_member_incr);
+  if (g->d_member_cid) cudaFree(g->d_member_cid);
   if (g->d_order) cudaFree(g->d_order);
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_ph) cudaStreamDestroy(g->s_ph);
@@ -972,14 +1025,10 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   const bool dev_in = (flags & XLG_INPUT_DEVICE) != 0;
   const bool dev_out = (g->flags & XLG_OUT_DEVICE) != 0;
 
-  // clients whose zero-history window has passed may move to the tiled kernel
-  if (!g->dirty && !q15 && g->n_generic > 0 && !(g->flags & XLG_FORCE_GENERIC)) {
-    std::map<std::tuple<uint32_t, size_t, long long>, int> cnt;
+  // clients whose zero-history window has passed may move to a tiled / long class
+  if (!g->dirty && !q15) {
     for (const HostClient &h : g->clients)
-      if (h.active && h.kind == 0 && !h.tile_ineligible && h.zero_before <= g->S - h.hist)
-        cnt[std::make_tuple(h.D, h.T, h.hist)]++;
-    for (auto &kv : cnt)
-      if (kv.second >= kTileMinClients) {
+      if (h.active && h.pending_settle && h.zero_before <= g->S - h.hist) {
         g->dirty = true;
         break;
       }
@@ -1122,7 +1171,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     for (const auto &sh : kShapes) {
       int ctas = 0;
       for (TileClassHost &ch : g->classes) {
-        const int n_out = ho.n_out[ch.members[0]];
+        int n_out = 0;
+        for (int id : ch.real) n_out = std::max(n_out, ho.n_out[id]);
         if (n_out > 0) ctas += ((n_out + sh[0] * sh[1] - 1) / (sh[0] * sh[1])) * ch.k.n_groups;
       }
       if (ctas >= 2 * g->fir_sms) {
@@ -1146,15 +1196,22 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     int ctas = 0;
     size_t smem = 0;
     for (TileClassHost &ch : g->classes) {
-      const HostClient &h0 = g->clients[ch.members[0]];
-      const int n_out = ho.n_out[ch.members[0]];
+      int n_out = 0;
+      for (int id : ch.real) n_out = std::max(n_out, ho.n_out[id]);
       if (n_out <= 0) continue;
       TileClass k = ch.k;
-      // hist was already advanced above; recover this block's window start
-      k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
+      if (ch.merged) {
+        // earliest possible window start of this block (history = T-1); every member's
+        // window starts delta in [0, D) samples later, read on the device from BlkInfo
+        k.first = S - (long long)(ch.T - 1);
+      } else {
+        // identical alignment: hist was already advanced above; recover this block's start
+        const HostClient &h0 = g->clients[ch.real[0]];
+        k.first = (S + n) - h0.hist - (long long)ho.n_out[ch.real[0]] * (long long)h0.D;
+      }
       k.n_out = n_out;
       k.tiles = (n_out + KT - 1) / KT;
-      k.xs_len = (KT - 1) * k.Dp + k.L;
+      k.xs_len = (KT - 1) * k.Dp + k.L + (ch.merged ? k.D : 0);
       k.cta_begin = ctas;
       ctas += k.tiles * k.n_groups;
       smem = std::max(smem, (size_t)T_SMEM_FIXED + ((size_t)k.xs_len + 10) * sizeof(float2));
@@ -1169,9 +1226,9 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       const float2 *tt = (const float2 *)g->d_tile_taps;
 #define XL_LAUNCH_TILE(LO_, RK_)                                                                              \
   fir_tile_cf32_kernel<LO_, RK_><<<ctas, TileShape<LO_, RK_>::kThreads, smem, cs>>>(P, g->ring, mask, tt,      \
-                                                                                  g->d_members,              \
-                                                                                  g->d_member_incr, s.d_phases, \
-                                                                                  s.d_out, g->d_trace)
+                                                                                  g->d_members, g->d_member_cid, \
+                                                                                  g->d_member_incr, s.d_blk,   \
+                                                                                  s.d_phases, s.d_out, g->d_trace)
       if (lo == 32 && rk == 4)
         XL_LAUNCH_TILE(32, 4);
       else if (lo == 16 && rk == 4)
@@ -1192,8 +1249,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     memset(&P, 0, sizeof(P));
     int ctas = 0, max_out = 0, max_groups = 0;
     for (TileClassHost &ch : g->long_classes) {
-      const HostClient &h0 = g->clients[ch.members[0]];
-      const int n_out = ho.n_out[ch.members[0]];
+      const HostClient &h0 = g->clients[ch.real[0]];
+      const int n_out = ho.n_out[ch.real[0]];
       if (n_out <= 0) continue;
       TileClass k = ch.k;
       k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;

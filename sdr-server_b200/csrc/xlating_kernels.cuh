@@ -468,7 +468,8 @@ template <int LO, int RK>
 __global__ void __launch_bounds__(TileShape<LO, RK>::kThreads, TileShape<LO, RK>::kMinCtas)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
                      const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
-                     const float2 *__restrict__ member_incr, const float2 *__restrict__ phases,
+                     const int *__restrict__ member_cid, const float2 *__restrict__ member_incr,
+                     const BlkInfo *__restrict__ blk, const float2 *__restrict__ phases,
                      float2 *__restrict__ out, long long *__restrict__ trace) {
   using S = TileShape<LO, RK>;
   // optional per-CTA timeline (XLATING_B200_TRACE=1): start, staged, loop done, end
@@ -495,7 +496,6 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   const int tile = local - grp * K.tiles;
   const int k0 = tile * KT;
   const int D = K.D, Dp = K.Dp, L = K.L;
-  const int n_out = K.n_out;
   const int nchunks = (L + T_JC - 1) / T_JC;
 
   // bars[0..S): "stage is full" (TMA transaction count); bars[S..2S): "stage is free"
@@ -563,9 +563,23 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
-  // members are packed from the front of a group: a warp whose first client is a
-  // padding slot has nothing to compute (it still takes part in the barriers)
-  const bool warp_active = grp * T_CG + warp * S::kWarpClients < K.n_members;
+  // This thread's 8 clients form a subgroup with ONE window alignment: clients of a
+  // class share (D, T) but may have been attached at different stream positions, so
+  // their windows start delta = first_c - K.first samples (0 <= delta < D) into the
+  // tile and they may produce one output less.  Both come from the oscillator
+  // pre-pass's per-block record of the subgroup's first client (-1 = all padding).
+  int delta = 0, n_out_sub = 0;
+  {
+    const int cid0 = __ldg(member_cid + K.members_off + grp * T_CG + cbase);
+    if (cid0 >= 0) {
+      const BlkInfo b = blk[cid0];
+      delta = (int)(b.first - K.first);
+      n_out_sub = b.n_out;
+    }
+  }
+  // a warp whose subgroups are all padding has nothing to compute (it still takes
+  // part in the barriers)
+  const bool warp_active = __any_sync(0xffffffffu, n_out_sub > 0);
 
   if (K.natural) {
     mbar_wait(&bars[2 * T_STAGES], 0);
@@ -583,7 +597,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
 
   const float2 *xb[RK];
 #pragma unroll
-  for (int i = 0; i < RK; i++) xb[i] = xs + (o + LO * i) * Dp;
+  for (int i = 0; i < RK; i++) xb[i] = xs + (o + LO * i) * Dp + delta;
 
   for (int ch = 0; ch < nchunks; ch++) {
     const int s = ch % T_STAGES;
@@ -639,7 +653,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   // The oscillator table is [k][32 clients]: this thread's 8 clients are 64
   // contiguous bytes per output.  The loads of two outputs (and the clients' output
   // row offsets) are in flight together before the first use.
-  if (warp_active) {
+  if (n_out_sub > 0) {
     int off[T_RC];
     float4 inc[T_RC / 2];  // oscillator steps of the 8 clients, (re, im) pairs
     {
@@ -662,7 +676,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       float4 ph[EB][T_RC / 2];
 #pragma unroll
       for (int ii = 0; ii < EB; ii++) {
-        const int k = min(k0 + o + LO * (i2 + ii), n_out - 1);  // clamped: always a valid row
+        const int k = min(k0 + o + LO * (i2 + ii), n_out_sub - 1);  // clamped: always a valid row
 #pragma unroll
         for (int q = 0; q < T_RC / 2; q++) ph[ii][q] = __ldg(pt + (size_t)(k >> 1) * 16 + q);
       }
@@ -670,7 +684,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
       for (int ii = 0; ii < EB; ii++) {
         const int i = i2 + ii;
         const int k = k0 + o + LO * i;
-        if (k >= n_out) continue;
+        if (k >= n_out_sub) continue;
 #pragma unroll
         for (int q = 0; q < T_RC / 2; q++) {
           float2 p0 = make_float2(ph[ii][q].x, ph[ii][q].y), p1 = make_float2(ph[ii][q].z, ph[ii][q].w);

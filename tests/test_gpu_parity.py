@@ -544,3 +544,43 @@ def test_group_empty_blocks_and_client_churn(pkg):
         for cid, o in zip(ids, oracles):
             assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"blk {blk} c{cid}")
     g.close()
+
+
+def test_group_mixed_alignment_classes(pkg):
+    """Clients of one (D, T) attached at different stream positions have different
+    window alignments; with the natural input layout they still share a tiled class
+    (8-client subgroups of equal alignment), lone alignments stay on the generic
+    kernel.  Everything must match a reference filter created at the attach moment."""
+    rng = np.random.default_rng(71)
+    fs, max_in = 2016000, 32768
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 16400)
+    g = pkg.Group(fs, max_in)
+    ids, oracles = [], []
+
+    def attach(n, base):
+        for c in range(n):
+            center = base + 7000 * c
+            ids.append(g.add_client(42, taps, center))
+            oracles.append(po.OracleFilter(42, taps, center, fs, max_in))
+
+    def push(n):
+        x = rand_block(rng, "cu8", n)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for cid, o in zip(ids, oracles):
+            assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"client {cid} n={n}")
+
+    attach(10, -900000)
+    push(max_in)
+    for step, (n_new, n_samples) in enumerate([(3, 20002), (1, 1234), (2, 30000), (5, 32768), (2, 2 * 997)]):
+        attach(n_new, -500000 + 100000 * step)   # joins at a new alignment
+        push(n_samples)                          # first block: zero-history window -> generic
+        push(max_in)
+    for _ in range(3):
+        push(max_in)
+    kinds = [g.client_info(c)[1] for c in ids]
+    assert kinds.count(1) >= 10 + 3 + 2 + 5 + 2   # every alignment with >= 2 clients is tiled
+    assert kinds.count(0) >= 1                    # the lone one is not
+    hist = sorted({g.client_info(c)[0] for c in ids})
+    assert len(hist) >= 4                         # several different alignments are live
+    g.close()
