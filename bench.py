@@ -413,9 +413,20 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # rank 0 must print exactly ONE line on stdout; NCCL's version banner goes there too
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # rank 0 must print exactly ONE line on stdout, but NCCL prints its version banner
+        # there when the first communicator is created: point fd 1 at stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     pkg = importlib.import_module("sdr-server_b200")
     if wl["name"] == "cfg5":
         rc = run_broadcast_workload(args, wl, config, rank, world, local_rank)
