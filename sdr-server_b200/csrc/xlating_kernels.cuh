@@ -397,7 +397,7 @@ struct TileShape {
   static constexpr int kWarps = T_CG / kWarpClients;         // 4 or 2
   static constexpr int kThreads = kWarps * 32;               // 128 or 64
   static constexpr int kKT = LO * RK;                        // outputs per CTA
-  static constexpr int kMinCtas = LO == 32 ? 3 : 6;          // register budget hint for ptxas
+  static constexpr int kMinCtas = LO == 32 ? 3 : 4;          // shared memory allows 4 CTAs per SM: up to 255 registers
 };
 
 // One class = clients with identical (D, T, window alignment).  "Flat" tap index:
