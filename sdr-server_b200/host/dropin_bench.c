@@ -1,0 +1,95 @@
+/*
+ * host/dropin_bench.c -- the UNMODIFIED reference threading model on the drop-in ABI:
+ * one filter and one dsp thread per client (src/dsp_worker.c:41-88), every thread
+ * processing its own private copy of the same block sequence (src/queue.c:114), no
+ * batch binding.  Measures what sdr-server gets by only re-linking against
+ * libxlating_b200.so.
+ *
+ * usage: dropin_bench <clients> <blocks>      (2.016 Msps cu8, 48/96 ksps mixed)
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "lpf.h"
+#include "xlating.h"
+
+#define BLOCK 262144
+
+typedef struct {
+  xlating *filter;
+  uint8_t *blocks[4]; /* private copies, like the per-client queue nodes */
+  int n_blocks;
+  uint64_t outputs;
+} client_t;
+
+static void *dsp_thread(void *arg) {
+  client_t *c = (client_t *)arg;
+  xlating_cf32 *out = NULL;
+  size_t n = 0;
+  for (int b = 0; b < c->n_blocks; b++) {
+    process_native_cu8_cf32(c->blocks[b % 4], BLOCK, &out, &n, c->filter);
+    c->outputs += n;
+  }
+  return NULL;
+}
+
+int main(int argc, char **argv) {
+  const int n_clients = argc > 1 ? atoi(argv[1]) : 64;
+  const int n_blocks = argc > 2 ? atoi(argv[2]) : 50;
+  const uint32_t fs = 2016000;
+  uint8_t *master[4];
+  uint64_t s = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < 4; i++) {
+    master[i] = (uint8_t *)malloc(BLOCK);
+    for (int j = 0; j < BLOCK; j++) {
+      s ^= s << 13;
+      s ^= s >> 7;
+      s ^= s << 17;
+      master[i][j] = (uint8_t)s;
+    }
+  }
+  client_t *clients = (client_t *)calloc((size_t)n_clients, sizeof(client_t));
+  for (int c = 0; c < n_clients; c++) {
+    const uint32_t rate = (c % 2 == 0) ? 48000 : 96000;
+    float *taps = NULL;
+    size_t len = 0;
+    if (create_low_pass_filter(1.0f, fs, rate / 2, rate / 5, &taps, &len) != 0) return 1;
+    const int32_t center = (int32_t)(-(int32_t)fs / 2 + (int32_t)rate / 2 +
+                                     (int64_t)c * (fs - rate) / (n_clients > 1 ? n_clients - 1 : 1));
+    if (create_frequency_xlating_filter(fs / rate, taps, len, center, fs, BLOCK, &clients[c].filter) != 0) {
+      fprintf(stderr, "create failed for client %d\n", c);
+      return 1;
+    }
+    for (int i = 0; i < 4; i++) {
+      clients[c].blocks[i] = (uint8_t *)malloc(BLOCK);
+      memcpy(clients[c].blocks[i], master[i], BLOCK);
+    }
+    clients[c].n_blocks = n_blocks;
+  }
+  /* warm-up: one block each, sequentially */
+  for (int c = 0; c < n_clients; c++) {
+    xlating_cf32 *out = NULL;
+    size_t n = 0;
+    process_native_cu8_cf32(clients[c].blocks[0], BLOCK, &out, &n, clients[c].filter);
+  }
+  pthread_t *threads = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_clients);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int c = 0; c < n_clients; c++) pthread_create(&threads[c], NULL, dsp_thread, &clients[c]);
+  for (int c = 0; c < n_clients; c++) pthread_join(threads[c], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  uint64_t outputs = 0;
+  for (int c = 0; c < n_clients; c++) outputs += clients[c].outputs;
+  printf("{\"bench\": \"dropin_thread_per_client\", \"simd_status\": \"%s\", \"clients\": %d, \"blocks\": %d, "
+         "\"seconds\": %.4f, \"input_msps\": %.2f, \"calls_per_s\": %.0f, \"us_per_call_per_thread\": %.1f, "
+         "\"outputs\": %llu}\n",
+         SIMD_STATUS, n_clients, n_blocks, dt, n_blocks * (BLOCK / 2) / dt / 1e6, (double)n_clients * n_blocks / dt,
+         dt / n_blocks * 1e6, (unsigned long long)outputs);
+  for (int c = 0; c < n_clients; c++) destroy_xlating(clients[c].filter);
+  return 0;
+}
