@@ -132,6 +132,13 @@ int xlg_profile_read(xlg_group *g, xlg_profile *p, int reset);
  * which kernel currently serves the client (0 = generic, 1 = tiled, 2 = long-filter split-K). */
 int xlg_client_info(const xlg_group *g, int client_id, size_t *history, int *kernel_kind);
 
+/* Counters of the per-filter drop-in ABI (include/xlating.h) on `device`: process_*
+ * calls served so far, the number of launches (batches) they were combined into, and
+ * how many of them found their input already staged by another filter's call (the
+ * reference's per-client copies of one SDR block, src/queue.c:114).  -ENOENT before
+ * the first filter was created there. */
+int xlg_dropin_stats(int device, uint64_t *batches, uint64_t *calls, uint64_t *shared_inputs);
+
 #ifdef __cplusplus
 }
 #endif

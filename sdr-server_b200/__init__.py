@@ -48,7 +48,7 @@ REFERENCE_SYMBOLS = (
 GROUP_SYMBOLS = [
     "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_remove_client", "xlg_client_count", "xlg_submit",
     "xlg_wait", "xlg_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
-    "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info",
+    "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats",
 ]
 
 
@@ -139,6 +139,20 @@ _libc.free.argtypes = [C.c_void_p]
 
 def simd_status() -> str:
     return C.c_char_p.in_dll(lib(), "SIMD_STATUS").value.decode()
+
+
+def dropin_stats(device: int = 0):
+    """(batches, calls, shared_inputs) of the per-filter drop-in ABI on `device`: how many
+    launches the process_* calls made so far were combined into, and how many calls found
+    their input already staged by another filter (csrc/xlating_dropin.cu)."""
+    b, c, s = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    fn = lib().xlg_dropin_stats
+    fn.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    fn.restype = C.c_int
+    rc = fn(device, C.byref(b), C.byref(c), C.byref(s))
+    if rc != 0:
+        raise RuntimeError(f"xlg_dropin_stats -> {rc}")
+    return b.value, c.value, s.value
 
 
 def create_low_pass_filter(gain: float, sampling_freq: int, cutoff_freq: int, transition_width: int) -> np.ndarray:

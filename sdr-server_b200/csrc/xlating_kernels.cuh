@@ -33,6 +33,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "xlating_common.cuh"
+
 namespace xl {
 
 // ---------------------------------------------------------------------------
@@ -57,32 +59,6 @@ struct ClientDev {
   int ph_off;             // cf32 oscillator table: phase of EVEN output k lives at phases[ph_off + 32*(k/2)]
 };
 
-struct BlkInfo {
-  long long first;  // absolute sample index where output 0's window starts
-  int n_out;
-  int pad_;
-};
-
-// ---------------------------------------------------------------------------
-// small helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float2 cmul_unfused(float2 a, float2 b) {
-  // two products and one add per component, each rounded (what libgcc's __mulsc3
-  // does for finite operands in the reference's strict build)
-  float2 r;
-  r.x = __fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
-  r.y = __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
-  return r;
-}
-
-__device__ __forceinline__ short sat16(int v) {
-  return (short)max(-32768, min(32767, v));
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
 // ---------------------------------------------------------------------------
 // convert: raw interleaved I,Q scalars -> ring  (src/xlating.c:389-390, 399-400,
 // 409-410 for cf32; :418, :425, :432 for Q15).  All conversions are exact.
@@ -95,16 +71,13 @@ __global__ void convert_cf32_kernel(const void *__restrict__ raw, float2 *__rest
   float2 v;
   if (FMT == 0) {
     uchar2 u = reinterpret_cast<const uchar2 *>(raw)[i];
-    v.x = ((float)u.x - 127.5f) * 0.0078125f;
-    v.y = ((float)u.y - 127.5f) * 0.0078125f;
+    v = make_float2(cvt_cu8_f32(u.x), cvt_cu8_f32(u.y));
   } else if (FMT == 1) {
     char2 u = reinterpret_cast<const char2 *>(raw)[i];
-    v.x = (float)u.x * 0.0078125f;
-    v.y = (float)u.y * 0.0078125f;
+    v = make_float2(cvt_cs8_f32(u.x), cvt_cs8_f32(u.y));
   } else {
     short2 u = reinterpret_cast<const short2 *>(raw)[i];
-    v.x = (float)u.x * (1.0f / 32768.0f);
-    v.y = (float)u.y * (1.0f / 32768.0f);
+    v = make_float2(cvt_cs16_f32(u.x), cvt_cs16_f32(u.y));
   }
   ring[(unsigned)((unsigned long long)(S + i)) & mask] = v;
 }
@@ -117,12 +90,10 @@ __global__ void convert_q15_kernel(const void *__restrict__ raw, short2 *__restr
   short2 v;
   if (FMT == 0) {
     uchar2 u = reinterpret_cast<const uchar2 *>(raw)[i];
-    v.x = (short)(((int)u.x - 128) << 8);
-    v.y = (short)(((int)u.y - 128) << 8);
+    v = make_short2(cvt_cu8_q15(u.x), cvt_cu8_q15(u.y));
   } else if (FMT == 1) {
     char2 u = reinterpret_cast<const char2 *>(raw)[i];
-    v.x = (short)((int)u.x << 8);
-    v.y = (short)((int)u.y << 8);
+    v = make_short2(cvt_cs8_q15(u.x), cvt_cs8_q15(u.y));
   } else {
     v = reinterpret_cast<const short2 *>(raw)[i];
   }
@@ -130,12 +101,8 @@ __global__ void convert_q15_kernel(const void *__restrict__ raw, short2 *__restr
 }
 
 // ---------------------------------------------------------------------------
-// oscillator pre-pass.  The phase sequence does not depend on the data, only on
-// how many outputs each call produces, so it is computed apart from the FIR --
-// but it cannot be parallelised or put in closed form: parity is against the
-// reference's float recursion, which drifts 4e-3 rad per block
-// from exact math.  One thread per client replays it bit for bit and stores the
-// phase of every output of this block.
+// oscillator pre-pass (the recursion itself: xlating_common.cuh).  One thread per
+// client replays it and stores the phase of every (even) output of this block.
 // ---------------------------------------------------------------------------
 constexpr int P_THREADS = 32;   // one warp = one table group of 32 clients
 constexpr int P_QTHREADS = 64;  // Q15 variant (one thread per client)
@@ -148,7 +115,9 @@ constexpr int P_QTHREADS = 64;  // Q15 variant (one thread per client)
 // only thing on the critical path: the per-output store is one coalesced 256-byte
 // line for the whole warp, there is no shared memory, no barrier.  (Earlier
 // versions stored [client][k] rows -- first uncoalesced, then through a shared-
-// memory transpose with helper warps -- and spent 2/3 of their time on that.)
+// memory transpose with helper warps -- and spent 2/3 of their time on that; and
+// storing every output instead of every second one ran at 16.7 cycles/output,
+// because a lone warp can only keep ~32 stores in flight.)
 __global__ void __launch_bounds__(P_THREADS)
 phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, BlkInfo *__restrict__ blk,
                   float2 *__restrict__ phases, long long S, int n_in) {
@@ -158,47 +127,13 @@ phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, Blk
   if (!d->active) return;
   const int D = d->D;
   const long long first = S - d->hist;
-  const long long last_ok = S + n_in - d->T;  // last admissible window start (src/xlating.c:58-60)
-  int n_out = 0;
-  if (last_ok >= first) n_out = (int)((last_ok - first) / D) + 1;
-  if (n_out > d->out_cap) n_out = d->out_cap;  // cannot happen for input_len <= max_input_len
+  const int n_out = outputs_of_call(first, S, n_in, d->T, D, d->out_cap);
   BlkInfo b;
   b.first = first;
   b.n_out = n_out;
   b.pad_ = 0;
   blk[c] = b;
-  float2 p = d->phase;
-  const float2 inc = d->incr;
-  float2 *dst = phases + d->ph_off;
-  // Only the phases of EVEN outputs are stored; a consumer derives an odd output's
-  // phase with the same single unfused multiply the recursion itself performs
-  // (phase_{k+1} = phase_k * incr), so nothing changes numerically while the store
-  // rate and the table halve.  That matters because a lone warp can only keep ~32
-  // stores in flight: at one 256-byte store per output the recursion ran at 16.7
-  // cycles/output against its 10.75-cycle dependent chain.
-  // Unrolled 16 pairs: a global store keeps its source registers reserved until the
-  // LSU has read them (a long-scoreboard release, ~100+ cycles); with a short unroll
-  // the recursion stalls on that write-after-read hazard when the registers come round.
-  const int n_pairs = n_out >> 1;
-#pragma unroll 16
-  for (int m = 0; m < n_pairs; m++) {
-    dst[(size_t)m * 32] = p;   // phase of output 2m
-    p = cmul_unfused(p, inc);  // src/xlating.c:71 (output 2m+1)
-    p = cmul_unfused(p, inc);
-  }
-  if (n_out & 1) {
-    dst[(size_t)n_pairs * 32] = p;  // last (even-indexed) output
-    p = cmul_unfused(p, inc);
-  }
-  if (n_out > 0 && d->renorm) {
-    // src/xlating.c:73.  glibc's hypotf is (float)sqrt((double)x*x + (double)y*y)
-    // (verified on 5e7 random inputs); the products are exact in double.
-    const double m2 = (double)p.x * (double)p.x + (double)p.y * (double)p.y;
-    const float mag = (float)sqrt(m2);
-    p.x = __fdiv_rn(p.x, mag);
-    p.y = __fdiv_rn(p.y, mag);
-  }
-  d->phase = p;
+  d->phase = osc_chain_cf32<32>(d->phase, d->incr, phases + d->ph_off, n_out, d->renorm);
   d->hist = (S + n_in) - (first + (long long)n_out * D);  // src/xlating.c:76
 }
 
@@ -210,27 +145,16 @@ phase_q15_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict_
   ClientDev *d = cl + c;
   if (!d->active) return;
   const long long first = S - d->hist;
-  const long long last_ok = S + n_in - d->T;
-  int n_out = 0;
-  if (last_ok >= first) n_out = (int)((last_ok - first) / d->D) + 1;
-  if (n_out > d->out_cap) n_out = d->out_cap;
+  const int n_out = outputs_of_call(first, S, n_in, d->T, d->D, d->out_cap);
   BlkInfo b;
   b.first = first;
   b.n_out = n_out;
   b.pad_ = 0;
   blk[c] = b;
-  int pr = d->qph_re, pi = d->qph_im;
-  const int ir = d->qinc_re, ii = d->qinc_im;
-  short2 *row = qphases + d->out_off;
-  for (int k = 0; k < n_out; k++) {
-    row[k] = make_short2((short)pr, (short)pi);
-    const int nr = pr * ir - pi * ii;  // src/xlating.c:126-129 (no renormalisation)
-    const int ni = pr * ii + pi * ir;
-    pr = sat16(nr >> 15);
-    pi = sat16(ni >> 15);
-  }
-  d->qph_re = (short)pr;
-  d->qph_im = (short)pi;
+  const short2 ph = osc_chain_q15(make_short2(d->qph_re, d->qph_im), make_short2(d->qinc_re, d->qinc_im),
+                                  qphases + d->out_off, n_out);
+  d->qph_re = ph.x;
+  d->qph_im = ph.y;
   d->hist = (S + n_in) - (first + (long long)n_out * d->D);  // src/xlating.c:133
 }
 
@@ -238,12 +162,8 @@ phase_q15_kernel(ClientDev *__restrict__ cl, int n_clients, BlkInfo *__restrict_
 // generic FIR: any T, D, alignment, attach point.  CTA = 8 warps = 32 consecutive
 // outputs of one client; each warp owns 4 consecutive outputs, its lanes stride
 // over the taps (coalesced float2 loads of ring and taps through L1/L2) and the
-// partial dot products are combined with warp shuffles.
+// partial dot products are combined with warp shuffles (xlating_common.cuh).
 // ---------------------------------------------------------------------------
-constexpr int G_THREADS = 256;
-constexpr int G_OPW = 4;                       // outputs per warp
-constexpr int G_OPC = (G_THREADS / 32) * G_OPW;  // outputs per CTA
-
 __global__ void __launch_bounds__(G_THREADS)
 fir_generic_cf32_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restrict__ blk,
                         const float2 *__restrict__ ring, unsigned mask,
@@ -257,41 +177,8 @@ fir_generic_cf32_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restr
   if (kbase >= b.n_out) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = kbase + warp * G_OPW;
-  const int T = d->T, D = d->D;
-  const long long zb = d->zero_before;
-  const float2 *tp = taps + d->taps_off;
-
-  float2 acc[G_OPW];
-#pragma unroll
-  for (int i = 0; i < G_OPW; i++) acc[i] = make_float2(0.f, 0.f);
-
-  const long long w0 = b.first + (long long)k0 * D;
-  for (int j = lane; j < T; j += 32) {
-    const float2 t = __ldg(tp + j);
-#pragma unroll
-    for (int i = 0; i < G_OPW; i++) {
-      const long long ab = w0 + (long long)i * D + j;
-      float2 x = make_float2(0.f, 0.f);
-      if (ab >= zb) x = ring[(unsigned)((unsigned long long)ab) & mask];
-      acc[i].x = fmaf(x.x, t.x, acc[i].x);
-      acc[i].x = fmaf(-x.y, t.y, acc[i].x);
-      acc[i].y = fmaf(x.x, t.y, acc[i].y);
-      acc[i].y = fmaf(x.y, t.x, acc[i].y);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < G_OPW; i++) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, s);
-      acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, s);
-    }
-  }
-  // lane i finishes output i (every lane holds all four sums after the butterfly)
-  float2 mine = acc[0];
-#pragma unroll
-  for (int i = 1; i < G_OPW; i++)
-    if (lane == i) mine = acc[i];
+  const float2 mine = fir_warp_cf32(ring, mask, d->zero_before, taps + d->taps_off, d->T, d->D,
+                                    b.first + (long long)k0 * d->D, lane);
   const int k = k0 + lane;
   if (lane < G_OPW && k < b.n_out) {
     float2 ph = phases[d->ph_off + (size_t)(k >> 1) * 32];
@@ -300,9 +187,6 @@ fir_generic_cf32_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restr
   }
 }
 
-// Q15 integer path (src/xlating.c:92-140): int16 x int16 products accumulated in
-// int64 -- integer addition is associative, so the lane-split + shuffle reduction
-// is bit-exact against the reference's sequential loop.
 __global__ void __launch_bounds__(G_THREADS)
 fir_generic_q15_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restrict__ blk,
                        const short2 *__restrict__ ring, unsigned mask,
@@ -316,50 +200,11 @@ fir_generic_q15_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restri
   if (kbase >= b.n_out) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = kbase + warp * G_OPW;
-  const int T = d->T, D = d->D;
-  const long long zb = d->qzero_before;
-  const short2 *tp = qtaps + d->qtaps_off;
-
-  long long are[G_OPW], aim[G_OPW];
-#pragma unroll
-  for (int i = 0; i < G_OPW; i++) are[i] = aim[i] = 0;
-
-  const long long w0 = b.first + (long long)k0 * D;
-  for (int j = lane; j < T; j += 32) {
-    const short2 t = __ldg(tp + j);
-#pragma unroll
-    for (int i = 0; i < G_OPW; i++) {
-      const long long ab = w0 + (long long)i * D + j;
-      short2 x = make_short2(0, 0);
-      if (ab >= zb) x = ring[(unsigned)((unsigned long long)ab) & mask];
-      are[i] += (long long)((int)x.x * (int)t.x) - (long long)((int)x.y * (int)t.y);  // :114
-      aim[i] += (long long)((int)x.x * (int)t.y) + (long long)((int)x.y * (int)t.x);  // :115
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < G_OPW; i++) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      are[i] += __shfl_xor_sync(0xffffffffu, are[i], s);
-      aim[i] += __shfl_xor_sync(0xffffffffu, aim[i], s);
-    }
-  }
-  long long mre = are[0], mim = aim[0];
-#pragma unroll
-  for (int i = 1; i < G_OPW; i++)
-    if (lane == i) {
-      mre = are[i];
-      mim = aim[i];
-    }
+  const short2 mine = fir_warp_q15(ring, mask, d->qzero_before, qtaps + d->qtaps_off, d->T, d->D,
+                                   b.first + (long long)k0 * d->D, lane);
   const int k = k0 + lane;
-  if (lane < G_OPW && k < b.n_out) {
-    const int ar = sat16((int)(mre >> 15));  // :118-119
-    const int ai = sat16((int)(mim >> 15));
-    const short2 ph = qphases[d->out_off + k];
-    const int rr = ar * (int)ph.x - ai * (int)ph.y;  // :121-122
-    const int ri = ar * (int)ph.y + ai * (int)ph.x;
-    out[d->out_off + k] = make_short2(sat16(rr >> 15), sat16(ri >> 15));  // :123-124
-  }
+  if (lane < G_OPW && k < b.n_out)
+    out[d->out_off + k] = rotate_q15(mine, qphases[d->out_off + k]);  // src/xlating.c:121-124
 }
 
 // ---------------------------------------------------------------------------

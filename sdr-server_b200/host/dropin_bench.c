@@ -5,9 +5,16 @@
  * batch binding.  Measures what sdr-server gets by only re-linking against
  * libxlating_b200.so.
  *
- * usage: dropin_bench <clients> <blocks>      (2.016 Msps cu8, 48/96 ksps mixed)
+ * usage: dropin_bench <clients> <blocks> [window]     (2.016 Msps cu8, 48/96 ksps mixed)
+ *
+ * window = 0: every dsp thread free-runs through its blocks (pure throughput).
+ * window = W > 0: no thread starts block b before every thread finished block b - W,
+ * i.e. the SDR callback with per-client queues of W blocks and back-pressure instead
+ * of the reference's drop-newest (src/queue.c:90-94).
  */
 #include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -16,10 +23,28 @@
 
 #include "lpf.h"
 #include "xlating.h"
+#include "xlating_group.h"
 
 #define BLOCK 262144
 
+static int g_window = 0, g_clients = 0;
+static atomic_int *g_done; /* blocks finished, per client */
+static atomic_int g_min_done;
+
+static void wait_for_window(int b) {
+  while (b - atomic_load(&g_min_done) >= g_window) {
+    int m = atomic_load(&g_done[0]);
+    for (int c = 1; c < g_clients; c++) {
+      const int v = atomic_load(&g_done[c]);
+      if (v < m) m = v;
+    }
+    if (m > atomic_load(&g_min_done)) atomic_store(&g_min_done, m);
+    if (b - m >= g_window) sched_yield();
+  }
+}
+
 typedef struct {
+  int id;
   xlating *filter;
   uint8_t *blocks[4]; /* private copies, like the per-client queue nodes */
   int n_blocks;
@@ -31,8 +56,12 @@ static void *dsp_thread(void *arg) {
   xlating_cf32 *out = NULL;
   size_t n = 0;
   for (int b = 0; b < c->n_blocks; b++) {
+    if (g_window > 0) wait_for_window(b);
+    /* every SDR block is new data, and every client holds the same bytes of it */
+    memcpy(c->blocks[b % 4] + 64, &b, sizeof(b));
     process_native_cu8_cf32(c->blocks[b % 4], BLOCK, &out, &n, c->filter);
     c->outputs += n;
+    atomic_store(&g_done[c->id], b + 1);
   }
   return NULL;
 }
@@ -40,6 +69,9 @@ static void *dsp_thread(void *arg) {
 int main(int argc, char **argv) {
   const int n_clients = argc > 1 ? atoi(argv[1]) : 64;
   const int n_blocks = argc > 2 ? atoi(argv[2]) : 50;
+  g_window = argc > 3 ? atoi(argv[3]) : 0;
+  g_clients = n_clients;
+  g_done = (atomic_int *)calloc((size_t)n_clients, sizeof(atomic_int));
   const uint32_t fs = 2016000;
   uint8_t *master[4];
   uint64_t s = 0x9E3779B97F4A7C15ull;
@@ -69,6 +101,7 @@ int main(int argc, char **argv) {
       memcpy(clients[c].blocks[i], master[i], BLOCK);
     }
     clients[c].n_blocks = n_blocks;
+    clients[c].id = c;
   }
   /* warm-up: one block each, sequentially */
   for (int c = 0; c < n_clients; c++) {
@@ -85,11 +118,14 @@ int main(int argc, char **argv) {
   const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   uint64_t outputs = 0;
   for (int c = 0; c < n_clients; c++) outputs += clients[c].outputs;
-  printf("{\"bench\": \"dropin_thread_per_client\", \"simd_status\": \"%s\", \"clients\": %d, \"blocks\": %d, "
+  uint64_t batches = 0, calls = 0, shared = 0;
+  xlg_dropin_stats(0, &batches, &calls, &shared); /* stays 0 with XLATING_B200_DROPIN=group */
+  printf("{\"bench\": \"dropin_thread_per_client\", \"simd_status\": \"%s\", \"clients\": %d, \"blocks\": %d, \"window\": %d, "
          "\"seconds\": %.4f, \"input_msps\": %.2f, \"calls_per_s\": %.0f, \"us_per_call_per_thread\": %.1f, "
-         "\"outputs\": %llu}\n",
-         SIMD_STATUS, n_clients, n_blocks, dt, n_blocks * (BLOCK / 2) / dt / 1e6, (double)n_clients * n_blocks / dt,
-         dt / n_blocks * 1e6, (unsigned long long)outputs);
+         "\"outputs\": %llu, \"launch_batches\": %llu, \"engine_calls\": %llu, \"shared_inputs\": %llu}\n",
+         SIMD_STATUS, n_clients, n_blocks, g_window, dt, n_blocks * (BLOCK / 2) / dt / 1e6, (double)n_clients * n_blocks / dt,
+         dt / n_blocks * 1e6, (unsigned long long)outputs, (unsigned long long)batches, (unsigned long long)calls,
+         (unsigned long long)shared);
   for (int c = 0; c < n_clients; c++) destroy_xlating(clients[c].filter);
   return 0;
 }

@@ -512,6 +512,75 @@ def test_dropin_many_filters_thread_per_client(pkg):
         f.close()
 
 
+def test_dropin_combined_calls_mixed_paths_formats_sizes(pkg):
+    """Calls that arrive together are combined into one launch (csrc/xlating_dropin.cu):
+    a batch may mix input formats, the cf32 and the Q15 path, filter shapes and ragged
+    call sizes, and the result must not depend on how the calls were batched."""
+    import threading
+    rng = np.random.default_rng(71)
+    fs, max_in = 2016000, 40000
+    shapes = [(42, 24000, 9600, -312000), (21, 48000, 19200, 400000), (7, 100000, 60000, 0), (3, 300000, 200000, -7)]
+    fmts = ["cu8", "cs8", "cs16"]
+    sizes = [40000, 2, 39998, 1234, 0, 20000, 36]  # ragged, incl. too-short (test_xlating.c:63-81) and empty calls
+    jobs = []
+    for i in range(18):
+        D, cutoff, tw, center = shapes[i % len(shapes)]
+        fmt, q15 = fmts[i % 3], (i % 5 == 1)
+        taps = pkg.create_low_pass_filter(1.0, fs, cutoff, tw)
+        f = pkg.XlatingFilter(D, taps, center + 1000 * i, fs, max_in)
+        o = po.OracleFilter(D, taps, center + 1000 * i, fs, max_in)
+        blocks = [rand_block(rng, fmt, sizes[(b + i) % len(sizes)]) for b in range(6)]
+        ref = [(o.process_q15(fmt, x) if q15 else o.process_cf32(fmt, x)) for x in blocks]
+        jobs.append((f, fmt, q15, blocks, ref))
+    b0, c0, _ = pkg.dropin_stats()
+    errors = []
+    barrier = threading.Barrier(len(jobs))
+
+    def dsp_thread(i):
+        f, fmt, q15, blocks, ref = jobs[i]
+        try:
+            for b, x in enumerate(blocks):
+                barrier.wait()  # arrive together, like the dsp threads woken by one sdr_callback
+                if q15:
+                    np.testing.assert_array_equal(f.process_q15(fmt, x), ref[b], err_msg=f"client {i} block {b}")
+                else:
+                    y = f.process_cf32(fmt, x)
+                    assert len(y) == len(ref[b]), (i, b, len(y), len(ref[b]))
+                    if len(y):
+                        assert_cf32_close(y, ref[b], f"client {i} block {b}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=dsp_thread, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+    b1, c1, _ = pkg.dropin_stats()
+    n_calls = sum(1 for (_, _, _, blocks, _) in jobs for x in blocks if len(x) >= 2)
+    assert c1 - c0 == n_calls            # every non-empty call went through the engine ...
+    assert 0 < b1 - b0 <= n_calls        # ... in at most that many launches
+    for f, *_ in jobs:
+        f.close()
+
+
+def test_dropin_private_group_model(pkg, monkeypatch):
+    """XLATING_B200_DROPIN=group: each filter a private one-client batch group (the
+    older model, kept for A/B measurements) -- same results."""
+    monkeypatch.setenv("XLATING_B200_DROPIN", "group")
+    rng = np.random.default_rng(73)
+    fs, max_in = 2016000, 32768
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 9600)
+    f = pkg.XlatingFilter(42, taps, -312000, fs, max_in)
+    o = po.OracleFilter(42, taps, -312000, fs, max_in)
+    for n in (max_in, 1000, max_in):
+        x = rand_block(rng, "cu8", n)
+        assert_cf32_close(f.process_cf32("cu8", x), o.process_cf32("cu8", x), f"n={n}")
+    f.close()
+
+
 def test_group_empty_blocks_and_client_churn(pkg):
     """zero-length blocks, removing every client, re-adding, growing the arenas"""
     rng = np.random.default_rng(61)
