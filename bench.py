@@ -377,6 +377,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true",
+                    help="skip the thread-per-client run of the unmodified per-filter ABI (bin/dropin_bench)")
     ap.add_argument("--no-partition", action="store_true",
                     help="do not reserve 8 SMs (green context) for the oscillator pre-pass")
     args = ap.parse_args()
@@ -623,6 +625,23 @@ def main():
             line["cpu_baseline"] = cpu_arm(wl, budget_s=args.cpu_seconds)
         except Exception as ex:  # the GPU number stands on its own
             line["cpu_baseline"] = {"error": repr(ex)}
+    if not args.no_dropin and world == 1 and args.workload == "cfg2" and args.taps == "default":
+        # The same workload through the reference's UNMODIFIED per-filter ABI and threading
+        # model (one filter + one dsp thread per client, private copies of every block,
+        # src/dsp_worker.c:41-88): what sdr-server gets by re-linking only.  Not the headline
+        # (that is e2e, the batch binding); reported so that the two can be compared.
+        try:
+            exe = os.path.join(ROOT, "sdr-server_b200", "bin", "dropin_bench")
+            out = subprocess.run([exe, str(len(wl["plan"])), "40", "4"], capture_output=True, text=True,
+                                 timeout=120).stdout
+            d = json.loads(out.strip().splitlines()[-1])
+            line["dropin_abi"] = {"value": d["input_msps"], "unit": "MS/s", "clients": d["clients"],
+                                  "threads": d["clients"], "blocks": d["blocks"], "queue_window": d["window"],
+                                  "calls_per_s": d["calls_per_s"], "launch_batches": d["launch_batches"],
+                                  "shared_inputs": d["shared_inputs"], "engine_calls": d["engine_calls"],
+                                  "note": "process_native_cu8_cf32 from one thread per client (host/dropin_bench.c)"}
+        except Exception as ex:
+            line["dropin_abi"] = {"error": repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -23,8 +23,8 @@
 #include <string.h>
 
 #include <atomic>
-#include <condition_variable>
 #include <mutex>
+#include <thread>
 
 namespace xl {
 
@@ -65,7 +65,7 @@ inline uint64_t block_hash(const void *data, size_t n) {
 
 class BlockCache {
  public:
-  static constexpr int kSlots = 32;  // dsp threads drift apart by a few blocks; 32 x one block of memory is nothing
+  static constexpr int kSlots = 32;    // dsp threads drift apart by a few blocks; 32 x one block of memory is nothing
   static constexpr int kPrivate = -1;  // acquire(): no shared entry, use the caller's own path
 
   explicit BlockCache(const BlockCacheOps &ops) : ops_(ops) {}
@@ -78,110 +78,144 @@ class BlockCache {
 
   // Returns the slot of an entry holding exactly input[0, bytes) -- found or newly
   // published -- with one reference taken, or kPrivate.
+  //
+  // The hit path takes no lock: when an SDR block lands, every dsp thread but one
+  // arrives here within microseconds looking for the same entry, and a mutex (or a
+  // condition-variable broadcast) would hand them through one at a time.  A reader
+  // pins an entry with refs++ and then re-checks that it is still the entry it
+  // wanted; the recycler closes an entry (state = filling) and then checks refs == 0.
+  // Both sides use sequentially consistent operations, so at least one of them sees
+  // the other (Dekker) and an entry is never recycled under a reader.
   int acquire(const void *input, size_t bytes) {
     const uint64_t hash = block_hash(input, bytes);
-    std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
-      Entry *m = nullptr;
-      for (Entry &e : slots_)
-        if (e.state != kEmpty && e.bytes == bytes && e.hash == hash) {
-          m = &e;
-          break;
-        }
-      if (m != nullptr) {
-        if (m->state == kFilling) {  // another caller is publishing these bytes right now
-          cv_.wait(lk);
+      int filling = -1;
+      bool raced = false;
+      for (int i = 0; i < kSlots && !raced; i++) {
+        Entry &e = slots_[i];
+        const int st = e.state.load(std::memory_order_acquire);
+        if (st == kEmpty || e.hash.load(std::memory_order_relaxed) != hash ||
+            e.bytes.load(std::memory_order_relaxed) != bytes)
+          continue;
+        if (st == kFilling) {  // another caller is publishing these bytes right now
+          filling = i;
           continue;
         }
-        m->refs++;
-        m->stamp = ++clock_;
-        lk.unlock();
-        if (memcmp(m->host, input, bytes) == 0) {
-          hits_++;
-          return (int)(m - slots_);
+        e.refs.fetch_add(1);
+        if (e.state.load() == kReady && e.hash.load() == hash && e.bytes.load() == bytes) {
+          // pinned: host/dev/bytes cannot change while refs > 0
+          e.stamp.store(clock_.fetch_add(1) + 1, std::memory_order_relaxed);
+          if (memcmp(e.host, input, bytes) == 0) {
+            hits_.fetch_add(1, std::memory_order_relaxed);
+            return i;
+          }
+          e.refs.fetch_sub(1);  // hash collision
+          return kPrivate;
         }
-        lk.lock();  // hash collision
-        m->refs--;
-        return kPrivate;
+        e.refs.fetch_sub(1);  // the entry was being recycled: look again
+        raced = true;
       }
-      // publish: an empty entry, else the least recently used unreferenced one
+      if (raced) continue;
+      if (filling >= 0) {
+        // ~20 us (one memcpy + one async copy launch by the publisher); yield, do not sleep
+        while (slots_[filling].state.load(std::memory_order_acquire) == kFilling) std::this_thread::yield();
+        continue;
+      }
+      // ---- publish ----
       Entry *v = nullptr;
-      for (Entry &e : slots_)
-        if (e.state == kEmpty) {
-          v = &e;
-          break;
-        }
-      if (v == nullptr)
+      {
+        std::lock_guard<std::mutex> lk(mu_);  // one publisher at a time
+        bool appeared = false;
         for (Entry &e : slots_)
-          if (e.state == kReady && e.refs == 0 && (v == nullptr || e.stamp < v->stamp)) v = &e;
-      if (v == nullptr) return kPrivate;
-      if (v->cap < bytes) {
-        if (v->host != nullptr) ops_.release(ops_.ctx, v->host, v->dev);
-        v->host = v->dev = nullptr;
-        v->cap = 0;
-        v->state = kEmpty;
-        if (ops_.alloc(ops_.ctx, bytes, &v->host, &v->dev) != 0) return kPrivate;
-        v->cap = bytes;
+          if (e.state.load() != kEmpty && e.hash.load() == hash && e.bytes.load() == bytes) appeared = true;
+        if (appeared) continue;  // another publisher got there first: take the hit path
+        for (Entry &e : slots_)
+          if (e.state.load() == kEmpty) {
+            v = &e;
+            v->state.store(kFilling);
+            break;
+          }
+        while (v == nullptr) {
+          // least recently used unreferenced entry; close it, then make sure no reader got in
+          Entry *cand = nullptr;
+          for (Entry &e : slots_)
+            if (e.state.load() == kReady && e.refs.load() == 0 && !e.skip &&
+                (cand == nullptr || e.stamp.load() < cand->stamp.load()))
+              cand = &e;
+          if (cand == nullptr) break;
+          cand->state.store(kFilling);
+          if (cand->refs.load() == 0) {
+            v = cand;
+          } else {
+            cand->state.store(kReady);
+            cand->skip = true;  // busy after all: not this round
+          }
+        }
+        for (Entry &e : slots_) e.skip = false;
+        if (v == nullptr) return kPrivate;
+        // v is closed (kFilling): readers of its old contents back off, nobody else writes it
+        if (v->cap < bytes) {
+          if (v->host != nullptr) ops_.release(ops_.ctx, v->host, v->dev);
+          v->host = v->dev = nullptr;
+          v->cap = 0;
+          if (ops_.alloc(ops_.ctx, bytes, &v->host, &v->dev) != 0) {
+            v->hash.store(0);
+            v->bytes.store(0);
+            v->state.store(kEmpty);
+            return kPrivate;
+          }
+          v->cap = bytes;
+        }
+        v->hash.store(hash);
+        v->bytes.store(bytes);
+        v->refs.fetch_add(1);  // not store: late readers of the old contents may still be backing off
+        v->stamp.store(clock_.fetch_add(1) + 1);
       }
-      v->state = kFilling;
-      v->hash = hash;
-      v->bytes = bytes;
-      v->refs = 1;
-      v->stamp = ++clock_;
-      const int slot = (int)(v - slots_);
-      lk.unlock();
       memcpy(v->host, input, bytes);
-      const int rc = ops_.upload(ops_.ctx, slot, v->host, v->dev, bytes);
-      lk.lock();
-      if (rc != 0) {
-        v->state = kEmpty;
-        v->refs = 0;
-        cv_.notify_all();
+      const int slot = (int)(v - slots_);
+      if (ops_.upload(ops_.ctx, slot, v->host, v->dev, bytes) != 0) {
+        v->refs.fetch_sub(1);
+        v->hash.store(0);
+        v->bytes.store(0);
+        v->state.store(kEmpty);
         return kPrivate;
       }
-      v->state = kReady;
-      publishes_++;
-      cv_.notify_all();
+      publishes_.fetch_add(1, std::memory_order_relaxed);
+      v->state.store(kReady);
       return slot;
     }
   }
 
-  void release(int slot) {
-    std::lock_guard<std::mutex> lk(mu_);
-    slots_[slot].refs--;
-  }
+  void release(int slot) { slots_[slot].refs.fetch_sub(1); }
 
   // valid while the caller holds a reference
   const void *device_ptr(int slot) const { return slots_[slot].dev; }
   const void *host_ptr(int slot) const { return slots_[slot].host; }
 
   void stats(uint64_t *hits, uint64_t *publishes) {
-    std::lock_guard<std::mutex> lk(mu_);
     *hits = hits_.load();
-    *publishes = publishes_;
+    *publishes = publishes_.load();
   }
   int referenced() {
-    std::lock_guard<std::mutex> lk(mu_);
     int n = 0;
-    for (Entry &e : slots_) n += e.refs;
+    for (Entry &e : slots_) n += e.refs.load();
     return n;
   }
 
  private:
   enum { kEmpty = 0, kFilling = 1, kReady = 2 };
   struct Entry {
-    void *host = nullptr, *dev = nullptr;
-    size_t cap = 0, bytes = 0;
-    uint64_t hash = 0, stamp = 0;
-    int state = kEmpty, refs = 0;
+    void *host = nullptr, *dev = nullptr;  // written only by the publisher that closed the entry
+    size_t cap = 0;
+    bool skip = false;                     // publisher-private (under mu_)
+    std::atomic<uint64_t> hash{0}, stamp{0};
+    std::atomic<size_t> bytes{0};
+    std::atomic<int> state{kEmpty}, refs{0};
   };
   BlockCacheOps ops_;
-  std::mutex mu_;
-  std::condition_variable cv_;
+  std::mutex mu_;  // serialises publishers (victim choice, reallocation)
   Entry slots_[kSlots];
-  uint64_t clock_ = 0;
-  std::atomic<uint64_t> hits_{0};  // bumped after the memcmp, outside the mutex
-  uint64_t publishes_ = 0;
+  std::atomic<uint64_t> clock_{0}, hits_{0}, publishes_{0};
 };
 
 }  // namespace xl

@@ -16,12 +16,13 @@
  *   - the calling thread stages its input into the filter's pinned buffer
  *     (the only per-call memcpy, done in parallel by the callers) and queues a
  *     request;
- *   - the first caller that finds a free launch lane becomes the leader: it takes
- *     every queued request (its own included), writes the request table, launches
- *     dropin_front_kernel + dropin_fir_kernel for the whole batch
- *     (dropin_kernels.cuh) and synchronises once; the others sleep on a condition
- *     variable until their request is marked done.  A lone caller is always its own
- *     leader, so the single-filter latency has no thread hand-off in it.
+ *   - the first caller that finds a free launch lane becomes the leader
+ *     (call_combiner.h): it takes every queued request (its own included), writes
+ *     the request table, launches dropin_front_kernel + dropin_fir_kernel for the
+ *     whole batch (dropin_kernels.cuh) and synchronises once; the others sleep, each
+ *     on its own condition variable, until their request is marked done.  A lone
+ *     caller is always its own leader, so the single-filter latency has no thread
+ *     hand-off in it.
  *
  * Inputs are read and outputs are written by the kernels directly in pinned host
  * memory (zero-copy over PCIe; outputs as full 256-byte lines), so a batch is two
@@ -56,6 +57,7 @@
 #include <vector>
 
 #include "block_cache.h"
+#include "call_combiner.h"
 #include "dropin_kernels.cuh"
 #include "taps_host.h"
 #include "xlating.h"
@@ -82,7 +84,7 @@ using namespace xl;
 namespace {
 
 constexpr int kMaxFilters = 4096;  // FilterDev table entries per device
-constexpr int kMaxLanes = 4;
+constexpr int kMaxLanes = CallCombiner::kMaxLanes;
 constexpr int kMaxBatch = 1024;    // requests per launch
 
 struct Lane {
@@ -90,18 +92,16 @@ struct Lane {
   DropinReq *h_req = nullptr;        // pinned, read by the front kernel over PCIe
   const DropinReq *d_req = nullptr;  // its device address
   int2 *d_batch = nullptr;           // (filter, q15) per request, written by the front kernel
-  bool busy = false;
 };
 
 struct Engine {
   int device = 0;
-  std::mutex mu;
-  std::vector<xlating *> pending;
+  CallCombiner *combiner = nullptr;
   Lane lanes[kMaxLanes];
   int n_lanes = 4;
   FilterDev *d_filters = nullptr;
+  std::mutex mu;  // guards free_slots
   std::vector<int> free_slots;
-  uint64_t batches = 0, calls = 0;
   // identical-input sharing
   BlockCache *cache = nullptr;
   cudaStream_t s_upload = nullptr;             // H2D of published blocks
@@ -175,14 +175,49 @@ struct xlating_t {
   DropinReq req;
   int req_out = 0;
   int req_slot = -1;  // block-cache entry the input is shared through, or -1 (private staging)
-  bool taken = false, done = false;
-  int status = 0;
-  std::condition_variable cv;  // signalled when the request is done, or when this caller should lead
+  CombinerCall call;  // user = this filter
 };
 
 namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Launch one batch on lane `lane` and wait for it (CallCombiner::RunBatch; called by the
+// batch's leader thread).
+int run_batch(void *ctx, int lane, CombinerCall *const *batch, int n_req) {
+  Engine *e = (Engine *)ctx;
+  Lane &L = e->lanes[lane];
+  cudaError_t err = cudaSetDevice(e->device);
+  if (err == cudaSuccess) {
+    int max_n = 0, max_out = 0;
+    unsigned slots = 0;  // shared inputs this batch reads: wait for their H2D
+    for (int i = 0; i < n_req; i++) {
+      const xlating *b = (const xlating *)batch[i]->user;
+      L.h_req[i] = b->req;
+      if (b->req.n > max_n) max_n = b->req.n;
+      if (b->req_out > max_out) max_out = b->req_out;
+      if (b->req_slot >= 0) slots |= 1u << b->req_slot;
+    }
+    for (int sl = 0; sl < BlockCache::kSlots && err == cudaSuccess; sl++)
+      if (slots & (1u << sl)) err = cudaStreamWaitEvent(L.stream, e->ev_slot[sl], 0);
+    const int n_osc = (n_req + 31) / 32;
+    const int cpr = (max_n + DF_SPB - 1) / DF_SPB;
+    if (err == cudaSuccess) {
+      dropin_front_kernel<<<n_osc + n_req * cpr, DF_THREADS, 0, L.stream>>>(e->d_filters, L.d_req, L.d_batch, n_req,
+                                                                            n_osc, cpr);
+      if (max_out > 0)
+        dropin_fir_kernel<<<dim3((max_out + G_OPC - 1) / G_OPC, n_req), G_THREADS, 0, L.stream>>>(e->d_filters,
+                                                                                                  L.d_batch);
+      err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(L.stream);
+  }
+  if (err != cudaSuccess) {
+    XL_LOG("drop-in batch of %d calls failed: %s", n_req, cudaGetErrorString(err));
+    return -EIO;
+  }
+  return 0;
+}
 
 int engine_get(int device, Engine **out) {
   std::lock_guard<std::mutex> lk(g_engines_mu);
@@ -240,94 +275,14 @@ int engine_get(int device, Engine **out) {
     CU_TRY(cudaMalloc(&L.d_batch, sizeof(int2) * kMaxBatch));
   }
   for (int i = kMaxFilters - 1; i >= 0; i--) e->free_slots.push_back(i);
+  e->combiner = new (std::nothrow) CallCombiner(e->n_lanes, kMaxBatch, run_batch, e);
+  if (e->combiner == nullptr) return -ENOMEM;
   g_engines[device] = e;
   *out = e;
   return 0;
 fail:
   // partially built engine: leave the (few) allocations to process teardown
   return rc;
-}
-
-// Launch one batch and wait for it.  Called by the leader WITHOUT the engine mutex.
-int run_batch(Engine *e, Lane &L, const std::vector<xlating *> &batch) {
-  cudaError_t err = cudaSetDevice(e->device);
-  if (err == cudaSuccess) {
-    const int n_req = (int)batch.size();
-    int max_n = 0, max_out = 0;
-    unsigned slots = 0;  // shared inputs this batch reads: wait for their H2D
-    for (int i = 0; i < n_req; i++) {
-      const xlating *b = batch[i];
-      L.h_req[i] = b->req;
-      if (b->req.n > max_n) max_n = b->req.n;
-      if (b->req_out > max_out) max_out = b->req_out;
-      if (b->req_slot >= 0) slots |= 1u << b->req_slot;
-    }
-    for (int sl = 0; sl < BlockCache::kSlots && err == cudaSuccess; sl++)
-      if (slots & (1u << sl)) err = cudaStreamWaitEvent(L.stream, e->ev_slot[sl], 0);
-    const int n_osc = (n_req + 31) / 32;
-    const int cpr = (max_n + DF_SPB - 1) / DF_SPB;
-    if (err == cudaSuccess) {
-      dropin_front_kernel<<<n_osc + n_req * cpr, DF_THREADS, 0, L.stream>>>(e->d_filters, L.d_req, L.d_batch, n_req,
-                                                                            n_osc, cpr);
-      if (max_out > 0)
-        dropin_fir_kernel<<<dim3((max_out + G_OPC - 1) / G_OPC, n_req), G_THREADS, 0, L.stream>>>(e->d_filters,
-                                                                                                  L.d_batch);
-      err = cudaGetLastError();
-    }
-    if (err == cudaSuccess) err = cudaStreamSynchronize(L.stream);
-  }
-  if (err != cudaSuccess) {
-    XL_LOG("drop-in batch of %zu calls failed: %s", batch.size(), cudaGetErrorString(err));
-    return -EIO;
-  }
-  return 0;
-}
-
-// Queue f->req and return when it has been served (by this thread as leader, or by another).
-int engine_run(xlating *f) {
-  Engine *e = f->e;
-  std::vector<xlating *> batch;
-  std::unique_lock<std::mutex> lk(e->mu);
-  f->taken = f->done = false;
-  e->pending.push_back(f);
-  while (!f->done) {
-    int lane = -1;
-    if (!f->taken)
-      for (int i = 0; i < e->n_lanes; i++)
-        if (!e->lanes[i].busy) {
-          lane = i;
-          break;
-        }
-    if (lane < 0) {
-      f->cv.wait(lk);
-      continue;
-    }
-    // leader: everything queued so far, in arrival order (own request included)
-    Lane &L = e->lanes[lane];
-    L.busy = true;
-    const size_t take = e->pending.size() < (size_t)kMaxBatch ? e->pending.size() : (size_t)kMaxBatch;
-    // (with more than kMaxBatch calls queued ahead of its own, this thread serves those
-    // first and its request stays queued for the next round)
-    batch.assign(e->pending.begin(), e->pending.begin() + (long)take);
-    e->pending.erase(e->pending.begin(), e->pending.begin() + (long)take);
-    for (xlating *b : batch) b->taken = true;
-    e->batches++;
-    e->calls += take;
-    lk.unlock();
-    const int rc = run_batch(e, L, batch);
-    lk.lock();
-    L.busy = false;
-    // wake exactly the callers served, plus one queued caller to lead the next batch on
-    // the lane that just became free (no broadcast: with hundreds of dsp threads asleep
-    // a notify_all per batch is a stampede on e->mu)
-    for (xlating *b : batch) {
-      b->status = rc;
-      b->done = true;
-      if (b != f) b->cv.notify_one();
-    }
-    if (!e->pending.empty() && e->pending.front() != f) e->pending.front()->cv.notify_one();
-  }
-  return f->status;
 }
 
 void filter_release(xlating *f) {
@@ -494,7 +449,7 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
   f->req.fmt = fmt;
   f->req.q15 = q15 ? 1 : 0;
   f->req_out = n_out;
-  const int rc = engine_run(f);
+  const int rc = e->combiner->run(&f->call);
   if (slot >= 0) e->cache->release(slot);
   // the samples are consumed whatever happened to the launch
   f->hist = (S + n) - (first + (long long)n_out * (long long)f->D);
@@ -528,6 +483,7 @@ int create_frequency_xlating_filter(uint32_t decimation, float *taps, size_t tap
     return -ENOMEM;
   }
   f->adopted_taps = taps;
+  f->call.user = f;
   int device = 0;
   const char *env = getenv("XLATING_B200_DEVICE");
   if (env != NULL) {
@@ -560,9 +516,10 @@ int xlg_dropin_stats(int device, uint64_t *batches, uint64_t *calls, uint64_t *s
   std::lock_guard<std::mutex> lk(g_engines_mu);
   auto it = g_engines.find(device);
   if (it == g_engines.end()) return -ENOENT;
-  std::lock_guard<std::mutex> lk2(it->second->mu);
-  if (batches != NULL) *batches = it->second->batches;
-  if (calls != NULL) *calls = it->second->calls;
+  uint64_t b = 0, c = 0;
+  it->second->combiner->stats(&b, &c);
+  if (batches != NULL) *batches = b;
+  if (calls != NULL) *calls = c;
   uint64_t hits = 0, publishes = 0;
   it->second->cache->stats(&hits, &publishes);
   if (shared_inputs != NULL) *shared_inputs = hits;

@@ -8,12 +8,12 @@
  * usage: dropin_bench <clients> <blocks> [window]     (2.016 Msps cu8, 48/96 ksps mixed)
  *
  * window = 0: every dsp thread free-runs through its blocks (pure throughput).
- * window = W > 0: no thread starts block b before every thread finished block b - W,
- * i.e. the SDR callback with per-client queues of W blocks and back-pressure instead
- * of the reference's drop-newest (src/queue.c:90-94).
+ * window = W > 0: an SDR thread delivers block b to all clients at once, and only after
+ * every client has finished block b - W: per-client queues of W blocks with
+ * back-pressure instead of the reference's drop-newest (src/queue.c:90-94).
  */
 #include <pthread.h>
-#include <sched.h>
+#include <semaphore.h>
 #include <stdatomic.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -27,20 +27,27 @@
 
 #define BLOCK 262144
 
-static int g_window = 0, g_clients = 0;
-static atomic_int *g_done; /* blocks finished, per client */
-static atomic_int g_min_done;
+static int g_window = 0, g_clients = 0, g_blocks = 0;
+/* the SDR thread: block p is delivered to every client queue (one semaphore per
+ * client, like the reference's one mutex + condition per queue, src/queue.c:87-112) once
+ * all clients have finished block p - window */
+static sem_t *g_queue;      /* per client: blocks delivered and not yet taken */
+static sem_t g_sdr;         /* posted when some block has been finished by every client */
+static atomic_int *g_finished; /* per block: clients that are done with it */
 
-static void wait_for_window(int b) {
-  while (b - atomic_load(&g_min_done) >= g_window) {
-    int m = atomic_load(&g_done[0]);
-    for (int c = 1; c < g_clients; c++) {
-      const int v = atomic_load(&g_done[c]);
-      if (v < m) m = v;
-    }
-    if (m > atomic_load(&g_min_done)) atomic_store(&g_min_done, m);
-    if (b - m >= g_window) sched_yield();
+static void *sdr_thread(void *arg) {
+  (void)arg;
+  for (int p = 0; p < g_blocks; p++) {
+    if (p >= g_window) sem_wait(&g_sdr); /* block p - window is complete (they complete in order) */
+    for (int c = 0; c < g_clients; c++) sem_post(&g_queue[c]);
   }
+  return NULL;
+}
+
+static void wait_for_block(int id) { sem_wait(&g_queue[id]); }
+
+static void finished_block(int b) {
+  if (atomic_fetch_add(&g_finished[b], 1) + 1 == g_clients) sem_post(&g_sdr);
 }
 
 typedef struct {
@@ -56,12 +63,12 @@ static void *dsp_thread(void *arg) {
   xlating_cf32 *out = NULL;
   size_t n = 0;
   for (int b = 0; b < c->n_blocks; b++) {
-    if (g_window > 0) wait_for_window(b);
+    if (g_window > 0) wait_for_block(c->id);
     /* every SDR block is new data, and every client holds the same bytes of it */
     memcpy(c->blocks[b % 4] + 64, &b, sizeof(b));
     process_native_cu8_cf32(c->blocks[b % 4], BLOCK, &out, &n, c->filter);
     c->outputs += n;
-    atomic_store(&g_done[c->id], b + 1);
+    if (g_window > 0) finished_block(b);
   }
   return NULL;
 }
@@ -71,7 +78,11 @@ int main(int argc, char **argv) {
   const int n_blocks = argc > 2 ? atoi(argv[2]) : 50;
   g_window = argc > 3 ? atoi(argv[3]) : 0;
   g_clients = n_clients;
-  g_done = (atomic_int *)calloc((size_t)n_clients, sizeof(atomic_int));
+  g_blocks = n_blocks;
+  g_finished = (atomic_int *)calloc((size_t)n_blocks, sizeof(atomic_int));
+  g_queue = (sem_t *)calloc((size_t)n_clients, sizeof(sem_t));
+  for (int c = 0; c < n_clients; c++) sem_init(&g_queue[c], 0, 0);
+  sem_init(&g_sdr, 0, 0);
   const uint32_t fs = 2016000;
   uint8_t *master[4];
   uint64_t s = 0x9E3779B97F4A7C15ull;
@@ -112,8 +123,11 @@ int main(int argc, char **argv) {
   pthread_t *threads = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_clients);
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_t sdr;
   for (int c = 0; c < n_clients; c++) pthread_create(&threads[c], NULL, dsp_thread, &clients[c]);
+  if (g_window > 0) pthread_create(&sdr, NULL, sdr_thread, NULL);
   for (int c = 0; c < n_clients; c++) pthread_join(threads[c], NULL);
+  if (g_window > 0) pthread_join(sdr, NULL);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   uint64_t outputs = 0;
