@@ -632,7 +632,7 @@ def main():
         # (that is e2e, the batch binding); reported so that the two can be compared.
         try:
             exe = os.path.join(ROOT, "sdr-server_b200", "bin", "dropin_bench")
-            out = subprocess.run([exe, str(len(wl["plan"])), "40", "4"], capture_output=True, text=True,
+            out = subprocess.run([exe, str(len(wl["plan"])), "40", "64"], capture_output=True, text=True,
                                  timeout=120).stdout
             d = json.loads(out.strip().splitlines()[-1])
             line["dropin_abi"] = {"value": d["input_msps"], "unit": "MS/s", "clients": d["clients"],

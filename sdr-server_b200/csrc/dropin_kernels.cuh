@@ -9,9 +9,9 @@
  * together from different threads are combined into one batch of "requests"
  * (filter, private input) and served by two kernels:
  *
- *   dropin_front_kernel   blocks [0, n_osc): one lane per request replays that
- *                         filter's oscillator for this call (the dependent chain,
- *                         scheduled first because it is the long pole);
+ *   dropin_front_kernel   blocks [0, n_osc): one warp (lane 0) per request replays
+ *                         that filter's oscillator for this call (the dependent
+ *                         chain, scheduled first because it is the long pole);
  *                         remaining blocks: convert each request's raw samples
  *                         (16 bytes per lane) into the filter's private ring in HBM.
  *   dropin_fir_kernel     the generic FIR (xlating_common.cuh) per request; each
@@ -62,6 +62,7 @@ struct DropinReq {
 constexpr int DF_THREADS = 256;
 constexpr int DF_SPT = 8;                        // complex samples per thread (16 bytes of cu8)
 constexpr int DF_SPB = DF_THREADS * DF_SPT;      // per block
+constexpr int DF_OSC_PER_BLOCK = 4;              // oscillator chains per block (one warp each)
 
 __device__ __forceinline__ void dropin_store(const DropinReq &q, const FilterDev *d, int i, float re, float im,
                                              short qre, short qim) {
@@ -113,11 +114,23 @@ __device__ __forceinline__ void dropin_convert8(const DropinReq &q, const Filter
 
 __global__ void __launch_bounds__(DF_THREADS)
 dropin_front_kernel(FilterDev *__restrict__ filters, const DropinReq *__restrict__ req, int2 *__restrict__ batch,
-                    int n_req, int n_osc_blocks, int conv_blocks_per_req) {
+                    int n_req, int n_osc_blocks, int conv_blocks_per_req, int osc_lanes) {
   if ((int)blockIdx.x < n_osc_blocks) {
-    // ---- oscillator lanes: one request each ----
-    if (threadIdx.x >= 32) return;
-    const int r = blockIdx.x * 32 + threadIdx.x;
+    // ---- oscillator: one request per WARP (lane 0), DF_OSC_PER_BLOCK warps per block ----
+    // Not one request per lane: every filter has its own table, so a warp with L active
+    // lanes issues L separate 8-byte stores per step, and a warp can only keep ~32 store
+    // transactions in flight -- measured on the batch engine's pre-pass, 32 uncoalesced
+    // lanes ran the chain 4x slower than its 10.75-cycle dependent latency.  A lone lane
+    // stays on that latency; the four warps land on the SM's four schedulers.
+    int r;
+    if (osc_lanes) {  // A/B variant: 32 requests per block, one per lane of warp 0
+      if (threadIdx.x >= 32) return;
+      r = blockIdx.x * 32 + threadIdx.x;
+    } else {
+      const int w = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) != 0 || w >= DF_OSC_PER_BLOCK) return;
+      r = blockIdx.x * DF_OSC_PER_BLOCK + w;
+    }
     if (r >= n_req) return;
     const DropinReq q = req[r];
     FilterDev *d = filters + q.filter;

@@ -108,6 +108,7 @@ struct Engine {
   cudaEvent_t ev_slot[BlockCache::kSlots] = {};  // "entry is in HBM", recorded at each publish
   std::atomic<int> live_filters{0};
   bool share_inputs = true;                    // XLATING_B200_SHARE=0 turns the cache off
+  bool osc_lanes = false;                      // XLATING_B200_OSC=lanes: oscillator chains share one warp (A/B)
 };
 
 constexpr size_t kShareMinBytes = 4096;  // smaller inputs are not worth hashing
@@ -200,11 +201,12 @@ int run_batch(void *ctx, int lane, CombinerCall *const *batch, int n_req) {
     }
     for (int sl = 0; sl < BlockCache::kSlots && err == cudaSuccess; sl++)
       if (slots & (1u << sl)) err = cudaStreamWaitEvent(L.stream, e->ev_slot[sl], 0);
-    const int n_osc = (n_req + 31) / 32;
+    const int osc_per_block = e->osc_lanes ? 32 : DF_OSC_PER_BLOCK;
+    const int n_osc = (n_req + osc_per_block - 1) / osc_per_block;
     const int cpr = (max_n + DF_SPB - 1) / DF_SPB;
     if (err == cudaSuccess) {
       dropin_front_kernel<<<n_osc + n_req * cpr, DF_THREADS, 0, L.stream>>>(e->d_filters, L.d_req, L.d_batch, n_req,
-                                                                            n_osc, cpr);
+                                                                            n_osc, cpr, e->osc_lanes ? 1 : 0);
       if (max_out > 0)
         dropin_fir_kernel<<<dim3((max_out + G_OPC - 1) / G_OPC, n_req), G_THREADS, 0, L.stream>>>(e->d_filters,
                                                                                                   L.d_batch);
@@ -256,6 +258,8 @@ int engine_get(int device, Engine **out) {
     if (e->n_lanes > kMaxLanes) e->n_lanes = kMaxLanes;
     env = getenv("XLATING_B200_SHARE");
     e->share_inputs = !(env != nullptr && strcmp(env, "0") == 0);
+    env = getenv("XLATING_B200_OSC");
+    e->osc_lanes = env != nullptr && strcmp(env, "lanes") == 0;
   }
   {
     CU_TRY(cudaStreamCreateWithFlags(&e->s_upload, cudaStreamNonBlocking));
