@@ -6,11 +6,13 @@
  * Why: the reference hands every client a private memcpy of the SAME SDR block
  * (src/tcp_server.c:262-269 -> src/queue.c:114) and every dsp thread then calls
  * process_* on its copy.  Behind the per-filter ABI the library is not told that
- * those C inputs are identical -- but it can find out: a caller hashes its input,
- * looks the hash up here, and if a block with the same bytes was published by
- * another caller it byte-compares against that copy (memcmp, so a hash collision
- * costs time, never correctness) and shares it.  The block then crosses PCIe once
- * instead of C times, and the C-1 staging memcpys are replaced by C-1 memcmps.
+ * those C inputs are identical -- but it can find out: a caller computes a key from
+ * 16 sampled 32-byte pieces of its input (constant time), looks the key up here, and
+ * byte-compares against every published block with that key (memcmp: exact, and it
+ * stops at the first differing byte, so a key collision costs almost nothing).  On a
+ * match it shares that block.  The block then crosses PCIe once instead of C times,
+ * and the C-1 staging memcpys are replaced by C-1 memcmps -- one pass over the input
+ * per call, as before.
  *
  * Entries are reference counted by the calls that use them and recycled LRU once
  * unreferenced.  Callers that find no free entry fall back to their private path.
@@ -37,26 +39,29 @@ struct BlockCacheOps {
   void *ctx;
 };
 
-// 4 independent multiply-mix lanes over 32-byte strides: ~1 cycle per 8 bytes.
-// Only a filter in front of memcmp, so quality matters for speed, not correctness.
-inline uint64_t block_hash(const void *data, size_t n) {
+// Key of a block: its length and 16 pieces of 32 bytes spread evenly over it (all of
+// it when shorter than 512 bytes).  Only a filter in front of memcmp -- blocks that
+// differ elsewhere get the same key and are told apart by the comparison.
+inline uint64_t block_key(const void *data, size_t n) {
   const unsigned char *p = (const unsigned char *)data;
-  uint64_t h[4] = {0x9E3779B97F4A7C15ull ^ n, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
   const uint64_t k = 0xFF51AFD7ED558CCDull;
-  size_t i = 0;
-  for (; i + 32 <= n; i += 32) {
+  uint64_t h[4] = {0x9E3779B97F4A7C15ull ^ n, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+  auto mix32 = [&](const unsigned char *q) {
     uint64_t w[4];
-    memcpy(w, p + i, 32);
+    memcpy(w, q, 32);
     for (int l = 0; l < 4; l++) {
       h[l] = (h[l] ^ w[l]) * k;
       h[l] ^= h[l] >> 29;
     }
-  }
-  uint64_t tail[4] = {0, 0, 0, 0};
-  memcpy(tail, p + i, n - i);
-  for (int l = 0; l < 4; l++) {
-    h[l] = (h[l] ^ tail[l]) * k;
-    h[l] ^= h[l] >> 32;
+  };
+  if (n >= 512) {
+    for (int i = 0; i < 16; i++) mix32(p + (size_t)i * (n - 32) / 15);
+  } else {
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) mix32(p + i);
+    unsigned char tail[32] = {0};
+    memcpy(tail, p + i, n - i);
+    mix32(tail);
   }
   uint64_t r = h[0];
   for (int l = 1; l < 4; l++) r = (r ^ h[l]) * 0xC4CEB9FE1A85EC53ull + l;
@@ -67,6 +72,7 @@ class BlockCache {
  public:
   static constexpr int kSlots = 32;    // dsp threads drift apart by a few blocks; 32 x one block of memory is nothing
   static constexpr int kPrivate = -1;  // acquire(): no shared entry, use the caller's own path
+  static_assert(kSlots <= 32, "acquire() keeps rejected entries in a 32-bit mask");
 
   explicit BlockCache(const BlockCacheOps &ops) : ops_(ops) {}
   ~BlockCache() {
@@ -87,14 +93,15 @@ class BlockCache {
   // Both sides use sequentially consistent operations, so at least one of them sees
   // the other (Dekker) and an entry is never recycled under a reader.
   int acquire(const void *input, size_t bytes) {
-    const uint64_t hash = block_hash(input, bytes);
+    const uint64_t hash = block_key(input, bytes);
+    uint32_t rejected = 0;  // entries with this key whose bytes turned out to differ
     for (;;) {
       int filling = -1;
       bool raced = false;
       for (int i = 0; i < kSlots && !raced; i++) {
         Entry &e = slots_[i];
         const int st = e.state.load(std::memory_order_acquire);
-        if (st == kEmpty || e.hash.load(std::memory_order_relaxed) != hash ||
+        if (st == kEmpty || (rejected & (1u << i)) || e.hash.load(std::memory_order_relaxed) != hash ||
             e.bytes.load(std::memory_order_relaxed) != bytes)
           continue;
         if (st == kFilling) {  // another caller is publishing these bytes right now
@@ -109,8 +116,9 @@ class BlockCache {
             hits_.fetch_add(1, std::memory_order_relaxed);
             return i;
           }
-          e.refs.fetch_sub(1);  // hash collision
-          return kPrivate;
+          e.refs.fetch_sub(1);  // same key, different bytes: another entry may still match
+          rejected |= 1u << i;
+          continue;
         }
         e.refs.fetch_sub(1);  // the entry was being recycled: look again
         raced = true;
@@ -126,8 +134,11 @@ class BlockCache {
       {
         std::lock_guard<std::mutex> lk(mu_);  // one publisher at a time
         bool appeared = false;
-        for (Entry &e : slots_)
-          if (e.state.load() != kEmpty && e.hash.load() == hash && e.bytes.load() == bytes) appeared = true;
+        for (int i = 0; i < kSlots; i++) {
+          Entry &e = slots_[i];
+          if (!(rejected & (1u << i)) && e.state.load() != kEmpty && e.hash.load() == hash && e.bytes.load() == bytes)
+            appeared = true;
+        }
         if (appeared) continue;  // another publisher got there first: take the hit path
         for (Entry &e : slots_)
           if (e.state.load() == kEmpty) {

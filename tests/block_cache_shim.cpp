@@ -45,7 +45,7 @@ void bc_stats(void *c, uint64_t *hits, uint64_t *publishes) { ((xl::BlockCache *
 int bc_referenced(void *c) { return ((xl::BlockCache *)c)->referenced(); }
 long bc_uploads() { return g_uploads.load(); }
 int bc_slots() { return xl::BlockCache::kSlots; }
-uint64_t bc_hash(const void *p, size_t n) { return xl::block_hash(p, n); }
+uint64_t bc_key(const void *p, size_t n) { return xl::block_key(p, n); }
 
 // n_threads "dsp threads" walk the same sequence of blocks (private copies of block
 // b = pool[b % pool]), some of them lagging behind; every acquired entry must hold

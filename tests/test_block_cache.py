@@ -29,8 +29,8 @@ def shim(tmp_path_factory):
     L.bc_referenced.argtypes = [C.c_void_p]
     L.bc_uploads.restype = C.c_long
     L.bc_slots.restype = C.c_int
-    L.bc_hash.restype = C.c_uint64
-    L.bc_hash.argtypes = [C.c_void_p, C.c_size_t]
+    L.bc_key.restype = C.c_uint64
+    L.bc_key.argtypes = [C.c_void_p, C.c_size_t]
     L.bc_stress.restype = C.c_long
     L.bc_stress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     return L
@@ -46,18 +46,47 @@ def stats(L, c):
     return h.value, p.value
 
 
-def test_hash_depends_on_every_byte_and_length(shim):
+def test_key_is_a_function_of_length_and_sampled_bytes(shim):
     rng = np.random.default_rng(1)
-    for n in (1, 7, 31, 32, 33, 100, 4096, 262144):
+    for n in (1, 7, 31, 32, 33, 100, 511, 512, 4096, 262144):
         a = rng.integers(0, 256, n, dtype=np.uint8)
-        h = shim.bc_hash(a.ctypes.data, n)
-        assert h == shim.bc_hash(a.copy().ctypes.data, n)
-        for pos in {0, n // 2, n - 1}:
+        k = shim.bc_key(a.ctypes.data, n)
+        assert k == shim.bc_key(a.copy().ctypes.data, n)
+        for pos in {0, n - 1}:                       # first and last byte are always sampled
             b = a.copy()
             b[pos] ^= 1
-            assert shim.bc_hash(b.ctypes.data, n) != h, (n, pos)
+            assert shim.bc_key(b.ctypes.data, n) != k, (n, pos)
+        if n < 512:                                  # short blocks are keyed on every byte
+            b = a.copy()
+            b[n // 2] ^= 1
+            assert shim.bc_key(b.ctypes.data, n) != k
         if n > 1:
-            assert shim.bc_hash(a.ctypes.data, n - 1) != h
+            assert shim.bc_key(a.ctypes.data, n - 1) != k
+
+
+def test_same_key_different_bytes_are_told_apart(shim):
+    """Blocks that differ only where the key does not look get the same key; the byte
+    comparison keeps them apart, and each is still shared with its own duplicates."""
+    c = shim.bc_new(None)
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, 262144, dtype=np.uint8)
+    variants = []
+    for v in range(5):
+        y = x.copy()
+        y[100] = v                                    # byte 100 is not sampled for this length
+        assert shim.bc_key(y.ctypes.data, y.nbytes) == shim.bc_key(x.ctypes.data, x.nbytes)
+        variants.append(y)
+    slots = [acquire(shim, c, y) for y in variants]
+    assert len(set(slots)) == 5 and min(slots) >= 0
+    again = [acquire(shim, c, y.copy()) for y in reversed(variants)]
+    assert again == list(reversed(slots))
+    for s_, y in zip(slots, variants):
+        assert shim.bc_matches(c, s_, y.ctypes.data, y.nbytes)
+    assert stats(shim, c) == (5, 5)
+    for s_ in slots + again:
+        shim.bc_release(c, s_)
+    assert shim.bc_referenced(c) == 0
+    shim.bc_delete(c)
 
 
 def test_identical_blocks_share_one_entry(shim):
