@@ -32,8 +32,8 @@
  *
  * Identical inputs.  The dsp threads of the reference all hold copies of the SAME
  * block.  With two or more filters alive a caller therefore first looks its input up
- * in a small content-addressed cache (block_cache.h: hash, then memcmp against the
- * published copy -- never trusting the hash): the first caller publishes the block
+ * in a small content-addressed cache (block_cache.h: a sampled key, then memcmp against
+ * the published copies with that key -- never trusting the key): the first caller publishes the block
  * (pinned copy + one async H2D), the others share its HBM copy, so the block crosses
  * PCIe once per SDR block instead of once per client.  Callers with unique data, or
  * arriving when every cache entry is in use, take the private zero-copy path.
