@@ -7,7 +7,9 @@
  * that the reference's callers -- src/dsp_worker.c:104,110-124,195-197,
  * src/main.c:10,23, test/test_xlating.c, test/perf_xlating.c -- compile and link
  * against libxlating_b200.so unchanged.  Behind them the arithmetic runs in
- * hand-written sm_100a CUDA kernels (sdr-server_b200/csrc/xlating_kernels.cuh);
+ * hand-written sm_100a CUDA kernels (sdr-server_b200/csrc/dropin_kernels.cuh, host side
+ * in csrc/xlating_dropin.cu: concurrent calls on different filters are combined into
+ * shared launches, identical input blocks are transferred once);
  * there is NO CPU fallback: if no CUDA device is usable, create fails with
  * -ENODEV and a "<3>" line on stderr.
  *

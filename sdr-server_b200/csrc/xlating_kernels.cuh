@@ -26,6 +26,9 @@
  *   fir_generic_*    any (T, D, alignment): one warp per 4 outputs, lanes split the
  *                    taps, warp-shuffle reduction; also the Q15 integer path
  *
+ * The arithmetic shared with the per-filter drop-in engine (conversions, oscillator
+ * recursion, generic FIR warp) lives in xlating_common.cuh.
+ *
  * Everything here is written for sm_100a only.
  */
 #pragma once
