@@ -110,18 +110,12 @@ class CallCombiner {
         calls_ += batch.size();
         q_.unlock();
         const int rc = fn_(ctx_, lane, batch.data(), (int)batch.size());
-        bool self_served = false;
-        for (CombinerCall *b : batch) {
-          if (b == c) {
-            self_served = true;
-            continue;
-          }
-          // notify under b->m: the owner cannot return (and destroy b) before we let go
-          std::lock_guard<std::mutex> g(b->m);
-          b->status = rc;
-          b->done = true;
-          b->cv.notify_one();
-        }
+        // Free the lane BEFORE waking the callers: every wake-up is a futex system call,
+        // and a batch of 20 would otherwise keep the lane idle for 20 of them.  The
+        // lane's vector goes with the lane, so keep the served calls in our own.
+        static thread_local std::vector<CombinerCall *> served;
+        if (served.capacity() < (size_t)max_batch_) served.reserve((size_t)max_batch_);  // the lane gets it back
+        served.swap(batch);
         q_.lock();
         busy_[lane] = false;
         if (!pending_.empty() && pending_.front() != c) {
@@ -133,10 +127,22 @@ class CallCombiner {
           next->lead = true;
           next->cv.notify_one();
         }
-        if (self_served) {
-          q_.unlock();
-          return rc;
+        q_.unlock();
+        bool self_served = false;
+        for (CombinerCall *b : served) {
+          if (b == c) {
+            self_served = true;
+            continue;
+          }
+          // notify under b->m: the owner cannot return (and destroy b) before we let go
+          std::lock_guard<std::mutex> g(b->m);
+          b->status = rc;
+          b->done = true;
+          b->cv.notify_one();
         }
+        served.clear();
+        if (self_served) return rc;
+        q_.lock();
         continue;
       }
       // no free lane, or another leader already took this call: sleep
