@@ -120,19 +120,50 @@ constexpr int G_THREADS = 256;
 constexpr int G_OPW = 4;                         // outputs per warp
 constexpr int G_OPC = (G_THREADS / 32) * G_OPW;  // outputs per CTA
 
+constexpr int G_STEPS = 4;  // tap steps (of 32 lanes) whose loads are issued together
+
 __device__ __forceinline__ float2 fir_warp_cf32(const float2 *__restrict__ ring, unsigned mask, long long zb,
                                                 const float2 *__restrict__ tp, int T, int D, long long w0,
                                                 int lane) {
   float2 acc[G_OPW];
 #pragma unroll
   for (int i = 0; i < G_OPW; i++) acc[i] = make_float2(0.f, 0.f);
-  for (int j = lane; j < T; j += 32) {
+  // A lone call is a fraction of one wave and purely load-latency bound (ncu: 11
+  // long-scoreboard stalls per issue slot with one step in flight), so the loads of
+  // G_STEPS tap steps are issued before their FMAs.  Loads are unconditional -- any
+  // masked index is inside the ring -- and samples before the attach point are zeroed
+  // by a select, which keeps the loop free of branches.  The accumulation order per
+  // lane is the sequential one.
+  int j = lane;
+  for (; j + 32 * (G_STEPS - 1) < T; j += 32 * G_STEPS) {
+    float2 t[G_STEPS], x[G_STEPS][G_OPW];
+#pragma unroll
+    for (int u = 0; u < G_STEPS; u++) {
+      t[u] = __ldg(tp + j + 32 * u);
+#pragma unroll
+      for (int i = 0; i < G_OPW; i++) {
+        const long long ab = w0 + (long long)i * D + j + 32 * u;
+        x[u][i] = ring[(unsigned)((unsigned long long)ab) & mask];
+        if (ab < zb) x[u][i] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G_STEPS; u++)
+#pragma unroll
+      for (int i = 0; i < G_OPW; i++) {
+        acc[i].x = fmaf(x[u][i].x, t[u].x, acc[i].x);
+        acc[i].x = fmaf(-x[u][i].y, t[u].y, acc[i].x);
+        acc[i].y = fmaf(x[u][i].x, t[u].y, acc[i].y);
+        acc[i].y = fmaf(x[u][i].y, t[u].x, acc[i].y);
+      }
+  }
+  for (; j < T; j += 32) {
     const float2 t = __ldg(tp + j);
 #pragma unroll
     for (int i = 0; i < G_OPW; i++) {
       const long long ab = w0 + (long long)i * D + j;
-      float2 x = make_float2(0.f, 0.f);
-      if (ab >= zb) x = ring[(unsigned)((unsigned long long)ab) & mask];
+      float2 x = ring[(unsigned)((unsigned long long)ab) & mask];
+      if (ab < zb) x = make_float2(0.f, 0.f);
       acc[i].x = fmaf(x.x, t.x, acc[i].x);
       acc[i].x = fmaf(-x.y, t.y, acc[i].x);
       acc[i].y = fmaf(x.x, t.y, acc[i].y);
@@ -165,13 +196,14 @@ __device__ __forceinline__ short2 fir_warp_q15(const short2 *__restrict__ ring, 
   long long are[G_OPW], aim[G_OPW];
 #pragma unroll
   for (int i = 0; i < G_OPW; i++) are[i] = aim[i] = 0;
+#pragma unroll 4
   for (int j = lane; j < T; j += 32) {
     const short2 t = __ldg(tp + j);
 #pragma unroll
     for (int i = 0; i < G_OPW; i++) {
       const long long ab = w0 + (long long)i * D + j;
-      short2 x = make_short2(0, 0);
-      if (ab >= zb) x = ring[(unsigned)((unsigned long long)ab) & mask];
+      short2 x = ring[(unsigned)((unsigned long long)ab) & mask];  // unconditional: any masked index is in the ring
+      if (ab < zb) x = make_short2(0, 0);
       are[i] += (long long)((int)x.x * (int)t.x) - (long long)((int)x.y * (int)t.y);  // :114
       aim[i] += (long long)((int)x.x * (int)t.y) + (long long)((int)x.y * (int)t.x);  // :115
     }
