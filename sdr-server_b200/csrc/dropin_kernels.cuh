@@ -36,7 +36,8 @@ struct FilterDev {
   short2 *qring;          // allocated on the first Q15 call
   const float2 *taps;     // reversed band-pass taps (:525-534)
   const short2 *qtaps;
-  float2 *phases;         // phase of output 2m at phases[m]
+  float2 *phases;         // phase of output 2m at phases[m], in HBM
+  const float2 *phases_host;  // the same table where the HOST writes it (device address of pinned memory)
   short2 *qphases;        // phase of output k at qphases[k]
   float2 *out;            // device address of the filter's pinned host output buffer (cf32)
   short2 *qout;           // same, Q15 (int16 re,im)
@@ -57,6 +58,10 @@ struct DropinReq {
   int n;            // complex samples in this call
   int fmt;          // XLG_FMT_*
   int q15;          // 1 = Q15 path
+  int osc_host;     // cf32 oscillator of this call: 0 = walked by a GPU lane; 1 = already walked by the host
+                    // (taps_host.c), table to be copied pinned -> HBM here; 2 = being walked by the host
+                    // while this kernel runs, the FIR kernel reads the pinned table itself
+  int n_out;        // outputs of this call (host mirror of the oscillator lane's count)
 };
 
 constexpr int DF_THREADS = 256;
@@ -134,7 +139,7 @@ dropin_front_kernel(FilterDev *__restrict__ filters, const DropinReq *__restrict
     if (r >= n_req) return;
     const DropinReq q = req[r];
     FilterDev *d = filters + q.filter;
-    batch[r] = make_int2(q.filter, q.q15);
+    batch[r] = make_int2(q.filter, q.q15 | (q.osc_host == 2 ? 2 : 0));
     const int D = d->D;
     const long long first = q.S - d->hist;
     const int n_out = outputs_of_call(first, q.S, q.n, d->T, D, d->out_cap);
@@ -145,7 +150,7 @@ dropin_front_kernel(FilterDev *__restrict__ filters, const DropinReq *__restrict
     d->blk = b;
     if (q.q15)
       d->qphase = osc_chain_q15(d->qphase, d->qincr, d->qphases, n_out);
-    else
+    else if (q.osc_host == 0)
       d->phase = osc_chain_cf32<1>(d->phase, d->incr, d->phases, n_out, 1);
     d->hist = (q.S + q.n) - (first + (long long)n_out * D);  // src/xlating.c:76, :133
     return;
@@ -158,9 +163,17 @@ dropin_front_kernel(FilterDev *__restrict__ filters, const DropinReq *__restrict
   if (threadIdx.x == 0) sq = req[r];
   __syncthreads();
   const DropinReq q = sq;
+  const FilterDev *d = filters + q.filter;
+  if (chunk == 0 && q.osc_host == 1 && !q.q15) {
+    // host-walked oscillator table: one coalesced pass pinned -> HBM (512 bytes per warp
+    // request) instead of one 32-byte PCIe read per FIR warp later
+    const int n16 = (((q.n_out + 1) >> 1) + 1) >> 1;  // 16-byte units, two table entries each
+    const uint4 *src = reinterpret_cast<const uint4 *>(d->phases_host);
+    uint4 *dst = reinterpret_cast<uint4 *>(d->phases);
+    for (int i = threadIdx.x; i < n16; i += DF_THREADS) dst[i] = src[i];
+  }
   const int base = chunk * DF_SPB + threadIdx.x * DF_SPT;
   if (base >= q.n) return;
-  const FilterDev *d = filters + q.filter;
   if (q.fmt == 0)
     dropin_convert8<0>(q, d, base);
   else if (q.fmt == 1)
@@ -184,7 +197,7 @@ dropin_fir_kernel(const FilterDev *__restrict__ filters, const int2 *__restrict_
   const long long w0 = b.first + (long long)k0 * d->D;
   // samples before the filter's creation (absolute index < 0) are the reference's
   // zero-initialised working buffer (src/xlating.c:556-565)
-  if (bq.y) {
+  if (bq.y & 1) {
     short2 *sq = reinterpret_cast<short2 *>(so);
     const short2 mine = fir_warp_q15(d->qring, d->mask, 0, d->qtaps, d->T, d->D, w0, lane);
     if (lane < G_OPW && k < b.n_out) sq[warp * G_OPW + lane] = rotate_q15(mine, d->qphases[k]);  // :121-124
@@ -193,7 +206,7 @@ dropin_fir_kernel(const FilterDev *__restrict__ filters, const int2 *__restrict_
   } else {
     const float2 mine = fir_warp_cf32(d->ring, d->mask, 0, d->taps, d->T, d->D, w0, lane);
     if (lane < G_OPW && k < b.n_out) {
-      float2 ph = d->phases[k >> 1];
+      float2 ph = ((bq.y & 2) ? d->phases_host : d->phases)[k >> 1];
       if (k & 1) ph = cmul_unfused(ph, d->incr);  // odd outputs: one step from the stored even phase
       so[warp * G_OPW + lane] = cmul_unfused(mine, ph);  // src/xlating.c:70
     }

@@ -69,3 +69,26 @@ void xl_client_consts_free(xl_client_consts *c) {
   c->rev_cf32 = NULL;
   c->rev_q15 = NULL;
 }
+
+void xl_osc_chain_cf32(float *phase_re, float *phase_im, float incr_re, float incr_im, float *table, int n_out) {
+  float pr = *phase_re, pi = *phase_im;
+  for (int k = 0; k < n_out; k++) {
+    if ((k & 1) == 0) {
+      table[k] = pr;
+      table[k + 1] = pi;
+    }
+    /* (pr + j pi)(ir + j ii), every product and sum rounded to float: what __mulsc3
+     * computes for finite operands in the reference's strict build (:71) */
+    const float nr = pr * incr_re - pi * incr_im;
+    const float ni = pr * incr_im + pi * incr_re;
+    pr = nr;
+    pi = ni;
+  }
+  if (n_out > 0) {
+    const float mag = hypotf(pr, pi); /* :73 */
+    pr = pr / mag;
+    pi = pi / mag;
+  }
+  *phase_re = pr;
+  *phase_im = pi;
+}

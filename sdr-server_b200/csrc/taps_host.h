@@ -25,6 +25,14 @@ int xl_client_consts_build(const float *lpf_taps, size_t taps_len, uint32_t deci
                            int32_t center_freq, uint32_t sampling_freq, xl_client_consts *out);
 void xl_client_consts_free(xl_client_consts *c);
 
+/* The float oscillator of one call on the host (src/xlating.c:70-73): n_out steps of
+ * phase *= incr starting from *phase, the phase of every EVEN output k stored as
+ * (re, im) at table[k] / table[k + 1], then -- if n_out > 0 -- the once-per-call
+ * renormalisation phase /= hypotf(re, im).  *phase is advanced.  Plain IEEE float
+ * arithmetic, unfused, exactly the reference's: a CPU core walks this dependent chain
+ * about three times faster than one GPU lane does. */
+void xl_osc_chain_cf32(float *phase_re, float *phase_im, float incr_re, float incr_im, float *table, int n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,14 @@ constexpr int kMaxFilters = 4096;  // FilterDev table entries per device
 constexpr int kMaxLanes = CallCombiner::kMaxLanes;
 constexpr int kMaxBatch = 1024;    // requests per launch
 
+// The cf32 oscillator of a call is a dependent chain of n_out steps.  A CPU core walks
+// it ~2.5x faster than a GPU lane (3 ns vs 7.5 ns per output), so it can run on the
+// calling thread (taps_host.c: xl_osc_chain_cf32, bit-identical arithmetic) into a pinned
+// table the FIR kernel reads; a lone filter's chain runs while the front kernel converts.
+// Measured (profiles/r1_dropin_threads.md): a lone 256 KiB call 60.7 -> 46.2 us; with many
+// callers the difference is inside the box-to-box noise.  XLATING_B200_OSC=device|lanes|host.
+constexpr bool kOscHostDefault = true;
+
 struct Lane {
   cudaStream_t stream = nullptr;
   DropinReq *h_req = nullptr;        // pinned, read by the front kernel over PCIe
@@ -109,6 +117,7 @@ struct Engine {
   std::atomic<int> live_filters{0};
   bool share_inputs = true;                    // XLATING_B200_SHARE=0 turns the cache off
   bool osc_lanes = false;                      // XLATING_B200_OSC=lanes: oscillator chains share one warp (A/B)
+  bool osc_host = kOscHostDefault;             // XLATING_B200_OSC=host|device: who walks the cf32 oscillator
 };
 
 constexpr size_t kShareMinBytes = 4096;  // smaller inputs are not worth hashing
@@ -172,6 +181,9 @@ struct xlating_t {
   const void *d_in = nullptr;  // device address of h_in (zero-copy)
   float2 *h_out = nullptr;
   short2 *h_qout = nullptr;
+  float *h_phases = nullptr;  // pinned oscillator table (host-walked chain), read by the FIR kernel
+  float ph_re = 1.0f, ph_im = 0.0f, inc_re = 0.0f, inc_im = 0.0f;  // host oscillator (src/xlating.c:543-544)
+  bool osc_deferred = false;  // this call's chain is still to be walked (by the batch leader)
   // the call in flight
   DropinReq req;
   int req_out = 0;
@@ -207,6 +219,13 @@ int run_batch(void *ctx, int lane, CombinerCall *const *batch, int n_req) {
     if (err == cudaSuccess) {
       dropin_front_kernel<<<n_osc + n_req * cpr, DF_THREADS, 0, L.stream>>>(e->d_filters, L.d_req, L.d_batch, n_req,
                                                                             n_osc, cpr, e->osc_lanes ? 1 : 0);
+      for (int i = 0; i < n_req; i++) {
+        xlating *b = (xlating *)batch[i]->user;  // its owner is asleep (or is this thread)
+        if (b->osc_deferred) {
+          xl_osc_chain_cf32(&b->ph_re, &b->ph_im, b->inc_re, b->inc_im, b->h_phases, b->req_out);
+          b->osc_deferred = false;
+        }
+      }
       if (max_out > 0)
         dropin_fir_kernel<<<dim3((max_out + G_OPC - 1) / G_OPC, n_req), G_THREADS, 0, L.stream>>>(e->d_filters,
                                                                                                   L.d_batch);
@@ -260,6 +279,8 @@ int engine_get(int device, Engine **out) {
     e->share_inputs = !(env != nullptr && strcmp(env, "0") == 0);
     env = getenv("XLATING_B200_OSC");
     e->osc_lanes = env != nullptr && strcmp(env, "lanes") == 0;
+    if (env != nullptr && strcmp(env, "host") == 0) e->osc_host = true;
+    if (env != nullptr && (strcmp(env, "device") == 0 || strcmp(env, "lanes") == 0)) e->osc_host = false;
   }
   {
     CU_TRY(cudaStreamCreateWithFlags(&e->s_upload, cudaStreamNonBlocking));
@@ -338,6 +359,7 @@ int filter_build(xlating *f, int device, uint32_t decimation, const float *taps,
   const size_t h_in_bytes = align_up((size_t)max_in * sizeof(int16_t), 256);  // cs16 is the widest input
   const size_t h_out_bytes = align_up((size_t)f->out_cap * sizeof(float2), 256);
   const size_t h_qout_bytes = align_up((size_t)f->out_cap * sizeof(short2), 256);
+  const size_t h_ph_bytes = align_up(((size_t)f->out_cap / 2 + 2) * sizeof(float2), 256);
   char *dm = nullptr, *hm = nullptr, *hm_dev = nullptr;
   CU_TRY(cudaSetDevice(device));
   CU_TRY(cudaMalloc(&f->d_mem, d_bytes));
@@ -345,18 +367,22 @@ int filter_build(xlating *f, int device, uint32_t decimation, const float *taps,
   CU_TRY(cudaMemset(dm, 0, o_taps));  // both rings start as the reference's zeroed working buffers (:556-565)
   CU_TRY(cudaMemcpy(dm + o_taps, k.rev_cf32, taps_len * sizeof(float2), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(dm + o_qtaps, k.rev_q15, taps_len * sizeof(short2), cudaMemcpyHostToDevice));
-  CU_TRY(cudaHostAlloc(&f->h_mem, h_in_bytes + h_out_bytes + h_qout_bytes, cudaHostAllocMapped));
+  CU_TRY(cudaHostAlloc(&f->h_mem, h_in_bytes + h_out_bytes + h_qout_bytes + h_ph_bytes, cudaHostAllocMapped));
   hm = (char *)f->h_mem;
   CU_TRY(cudaHostGetDevicePointer((void **)&hm_dev, f->h_mem, 0));
   f->h_in = hm;
   f->d_in = hm_dev;
   f->h_out = (float2 *)(hm + h_in_bytes);
   f->h_qout = (short2 *)(hm + h_in_bytes + h_out_bytes);
+  f->h_phases = (float *)(hm + h_in_bytes + h_out_bytes + h_qout_bytes);
+  f->inc_re = k.incr_re;
+  f->inc_im = k.incr_im;
   d.ring = (float2 *)(dm + o_ring);
   d.qring = (short2 *)(dm + o_qring);
   d.taps = (const float2 *)(dm + o_taps);
   d.qtaps = (const short2 *)(dm + o_qtaps);
   d.phases = (float2 *)(dm + o_ph);
+  d.phases_host = (const float2 *)(hm_dev + h_in_bytes + h_out_bytes + h_qout_bytes);
   d.qphases = (short2 *)(dm + o_qph);
   d.out = (float2 *)(hm_dev + h_in_bytes);
   d.qout = (short2 *)(hm_dev + h_in_bytes + h_out_bytes);
@@ -452,7 +478,21 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
   f->req.n = n;
   f->req.fmt = fmt;
   f->req.q15 = q15 ? 1 : 0;
+  f->req.osc_host = 0;
+  f->req.n_out = n_out;
   f->req_out = n_out;
+  f->osc_deferred = false;
+  if (e->osc_host && !q15) {
+    if (e->live_filters.load() >= 2) {
+      // many callers: each walks its own chain, in parallel, before queueing
+      xl_osc_chain_cf32(&f->ph_re, &f->ph_im, f->inc_re, f->inc_im, f->h_phases, n_out);
+      f->req.osc_host = 1;
+    } else {
+      // a lone filter: the chain is walked while the front kernel converts (run_batch)
+      f->osc_deferred = true;
+      f->req.osc_host = 2;
+    }
+  }
   const int rc = e->combiner->run(&f->call);
   if (slot >= 0) e->cache->release(slot);
   // the samples are consumed whatever happened to the launch

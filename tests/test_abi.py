@@ -139,3 +139,38 @@ def test_no_gpu_fails_loudly(pkg, capfd):
     with pytest.raises(ValueError) as e:
         pkg.XlatingFilter(5, np.zeros(0, dtype=np.float32), -12000, 48000, 2000)
     assert e.value.args[0] == -1
+
+
+def test_host_oscillator_is_the_reference_recursion(pkg):
+    """csrc/taps_host.c: xl_osc_chain_cf32 (the per-filter engine walks the float oscillator on
+    the calling thread) against a numpy float32 restatement of src/xlating.c:70-73: every
+    product and sum rounded to float, hypotf = (float)sqrt of the exact double sum."""
+    import math
+    fn = pkg.lib().xl_osc_chain_cf32
+    fn.argtypes = [C.POINTER(C.c_float)] * 2 + [C.c_float] * 2 + [C.POINTER(C.c_float), C.c_int]
+    fn.restype = None
+    f = np.float32
+
+    def restated(pr, pi, ir, ii, n):
+        table = []
+        for k in range(n):
+            if k % 2 == 0:
+                table += [pr, pi]
+            pr, pi = f(f(pr * ir) - f(pi * ii)), f(f(pr * ii) + f(pi * ir))
+        if n > 0:
+            mag = f(math.sqrt(float(pr) * float(pr) + float(pi) * float(pi)))
+            pr, pi = f(pr / mag), f(pi / mag)
+        return np.array(table, dtype=np.float32), pr, pi
+
+    for center, D in ((-312000, 42), (400000, 21), (7, 3)):
+        w = f(2 * math.pi * center / 2016000)
+        step = np.exp(np.complex64(1j) * f(-w * f(D)))
+        ir, ii = f(step.real), f(step.imag)
+        pr, pi = C.c_float(1.0), C.c_float(0.0)
+        epr, epi = f(1.0), f(0.0)
+        for n in (0, 1, 2, 7, 3121, 3120, 1):  # consecutive calls: the state carries over
+            table = (C.c_float * (n + 2))()
+            fn(C.byref(pr), C.byref(pi), ir, ii, table, n)
+            etable, epr, epi = restated(epr, epi, ir, ii, n)
+            assert np.array(table[:len(etable)], dtype=np.float32).tobytes() == etable.tobytes(), (center, n)
+            assert f(pr.value).tobytes() == epr.tobytes() and f(pi.value).tobytes() == epi.tobytes(), (center, n)
