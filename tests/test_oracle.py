@@ -140,6 +140,38 @@ def test_stream_bit_exact_vs_reference(fmt, fs, rate, tw, center):
         assert a.tobytes() == b.tobytes()
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_bit_exact_vs_reference(seed):
+    """Random (taps, decimation, centre, call sizes) -- arbitrary taps, not only designer
+    outputs, even and odd lengths, D from 1 to T: the restatement equals the compiled
+    reference bit for bit on both paths, call after call.  (D > T is left out: the
+    reference's history_offset underflows there, src/xlating.c:76.)"""
+    rng = np.random.default_rng(9000 + seed)
+    for _ in range(8):
+        T = int(rng.integers(1, 400))
+        D = int(rng.integers(1, T + 1))
+        fs = int(rng.choice([48000, 2016000, 10000000]))
+        center = int(rng.integers(-fs // 2, fs // 2))
+        taps = (rng.standard_normal(T) / max(T, 1) ** 0.5).astype(np.float32)
+        max_in = int(rng.integers(2, 6000)) * 2
+        fmt = str(rng.choice(["cu8", "cs8", "cs16"]))
+        filters = [po.OracleFilter(D, taps, center, fs, max_in), po.RefFilter(D, taps, center, fs, max_in),
+                   po.OracleFilter(D, taps, center, fs, max_in), po.RefFilter(D, taps, center, fs, max_in)]
+        for _call in range(6):
+            n = int(rng.integers(0, max_in // 2 + 1)) * 2
+            if fmt == "cs16":
+                x = rng.integers(-32768, 32768, n, dtype=np.int16)
+            elif fmt == "cs8":
+                x = rng.integers(-128, 128, n, dtype=np.int8)
+            else:
+                x = rng.integers(0, 256, n, dtype=np.uint8)
+            a, b = filters[0].process_cf32(fmt, x), filters[1].process_cf32(fmt, x)
+            assert a.tobytes() == b.tobytes(), (T, D, fs, center, fmt, n)
+            a, b = filters[2].process_q15(fmt, x), filters[3].process_q15(fmt, x)
+            assert a.tobytes() == b.tobytes(), (T, D, fs, center, fmt, n)
+
+
 @pytest.mark.skipif(not (po.ref_available("strict") and po.ref_available("release") and po.ref_available("avx")),
                     reason="oracle/_ref not built")
 def test_reference_builds_agree_only_norm_wise():
