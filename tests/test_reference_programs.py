@@ -95,3 +95,18 @@ def test_reference_perf_program_runs_on_the_gpu():
     # clock() sums CPU time over threads; the reference's own AVX build needs 1.6 ms per call here
     assert all(0.0 < t < 0.005 for t in times.values()), times
     print(r.stdout)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/xlating.h"), reason="needs /root/reference")
+def test_our_headers_declare_the_reference_prototypes(tmp_path):
+    """One translation unit including the reference's headers AND ours: C rejects a second
+    declaration of a function with a different type, so this compiles only if every
+    prototype in include/xlating.h and include/lpf.h equals the reference's
+    (src/xlating.h:8-38, src/lpf.h:6)."""
+    src = tmp_path / "both.c"
+    src.write_text('#include <stdlib.h>\n#include "/root/reference/src/lpf.h"\n#include "/root/reference/src/xlating.h"\n'
+                   f'#include "{ROOT}/include/lpf.h"\n#include "{ROOT}/include/xlating.h"\n'
+                   "int main(void) { return 0; }\n")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-c", str(src), "-o", str(tmp_path / "both.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
