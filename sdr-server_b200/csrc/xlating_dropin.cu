@@ -60,16 +60,12 @@
 #include "call_combiner.h"
 #include "dropin_kernels.cuh"
 #include "taps_host.h"
+#include "xl_log.h"
 #include "xlating.h"
 #include "xlating_group.h"
 
 using namespace xl;
 
-#define XL_LOG(...)                                   \
-  do {                                                \
-    fprintf(stderr, "<3>xlating_b200: " __VA_ARGS__); \
-    fprintf(stderr, "\n");                            \
-  } while (0)
 
 #define CU_TRY(expr)                                                                      \
   do {                                                                                    \

@@ -39,16 +39,12 @@
 #include <vector>
 
 #include "taps_host.h"
+#include "xl_log.h"
 #include "xlating_group.h"
 #include "xlating_kernels.cuh"
 
 using namespace xl;
 
-#define XL_LOG(...)                   \
-  do {                                \
-    fprintf(stderr, "<3>xlating_b200: " __VA_ARGS__); \
-    fprintf(stderr, "\n");            \
-  } while (0)
 
 #define CU_OK(expr)                                                                      \
   do {                                                                                   \
