@@ -110,3 +110,83 @@ def test_our_headers_declare_the_reference_prototypes(tmp_path):
     r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-c", str(src), "-o", str(tmp_path / "both.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+# ---------------------------------------------------------------------------
+# the reference's real per-client threads and queues (src/dsp_worker.c, src/queue.c,
+# unmodified) driven by oracle/ref_server_harness.c the way sdr_callback drives them
+# ---------------------------------------------------------------------------
+def run_harness(name, clients, blocks, queue_size, base, *extra, timeout=600):
+    r = subprocess.run([ref_program(name), str(clients), str(blocks), str(queue_size), str(base), *extra],
+                       capture_output=True, text=True, timeout=timeout)
+    return r
+
+
+def harness_plan(clients, fs=2016000):
+    """client layout of oracle/ref_server_harness.c (integer arithmetic as in C)"""
+    plan = []
+    for c in range(clients):
+        rate = 48000 if c % 2 == 0 else 96000
+        offset = -(fs // 2) + rate // 2 + c * (fs - rate) // (clients - 1 if clients > 1 else 1)
+        plan.append((rate, offset))
+    return plan
+
+
+def test_reference_dsp_workers_on_the_reference_match_the_oracle(tmp_path):
+    """Proves the harness: the files the reference's own dsp threads write (strict build)
+    are, bit for bit, what the restatement produces for the same blocks and clients."""
+    import json
+
+    import numpy as np
+
+    from oracle import pyoracle as po
+    clients, blocks = 6, 5
+    r = run_harness("server_harness_ref", clients, blocks, 8, tmp_path, "rtl", "dump")
+    assert r.returncode == 0, r.stderr[-400:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["clients"] == clients and line["blocks"] == blocks and line["input_msps"] > 0
+    raw = np.fromfile(tmp_path / "input.raw", dtype=np.uint8).reshape(blocks, 262144)
+    for c, (rate, offset) in enumerate(harness_plan(clients)):
+        taps = po.lpf_design(1.0, 2016000, rate // 2, rate // 5)
+        o = po.OracleFilter(2016000 // rate, taps, offset, 2016000, 262144)
+        want = np.concatenate([o.process_cf32("cu8", b) for b in raw])
+        got = np.fromfile(tmp_path / f"{c}.cf32", dtype=np.complex64)
+        assert got.tobytes() == want.tobytes(), c
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="this is the no-GPU behaviour")
+def test_reference_dsp_workers_on_this_library_fail_loudly_without_a_gpu(tmp_path):
+    r = run_harness("server_harness_b200", 2, 2, 4, tmp_path)
+    assert r.returncode != 0
+    assert "dsp_worker_start(client 0) -> -19" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run on a B200 is the driver's")
+def test_reference_dsp_workers_on_this_library_match_the_reference(tmp_path):
+    """The reference's own dsp_worker.c threads and queue.c queues, unmodified, calling into
+    libxlating_b200.so: every client's output file equals the one the same threads write on
+    the reference's own xlating.c (float tolerance of the contract), and the run is timed
+    against the reference's best CPU build."""
+    import json
+
+    import numpy as np
+
+    from util import assert_cf32_close
+    clients, blocks = 32, 12
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "b200").mkdir()
+    a = run_harness("server_harness_ref", clients, blocks, 16, tmp_path / "ref")
+    b = run_harness("server_harness_b200", clients, blocks, 16, tmp_path / "b200")
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr[-300:], b.stderr[-300:])
+    for c in range(clients):
+        want = np.fromfile(tmp_path / "ref" / f"{c}.cf32", dtype=np.complex64)
+        got = np.fromfile(tmp_path / "b200" / f"{c}.cf32", dtype=np.complex64)
+        assert_cf32_close(got, want, f"client {c}")
+    (tmp_path / "t1").mkdir()
+    (tmp_path / "t2").mkdir()
+    cpu = run_harness("server_harness_ref_avx", 64, 40, 64, tmp_path / "t1")
+    gpu = run_harness("server_harness_b200", 64, 40, 64, tmp_path / "t2")
+    assert cpu.returncode == 0 and gpu.returncode == 0
+    print("reference threads on the reference (AVX):", json.loads(cpu.stdout.strip().splitlines()[-1]))
+    print("reference threads on libxlating_b200   :", json.loads(gpu.stdout.strip().splitlines()[-1]))
