@@ -91,6 +91,13 @@ int xlg_wait(xlg_group *g, int64_t ticket);
  * and is available right after xlg_submit returns (it is computed on the host). */
 int xlg_output(xlg_group *g, int64_t ticket, int client_id, const void **out, size_t *out_len);
 
+/* Copy one client's output of a completed ticket into caller memory (cf32 pairs, or
+ * int16 pairs for XLG_PATH_Q15 tickets): waits for the ticket, then copies at most
+ * `cap` complex samples from wherever the result lives -- the pinned host arena, or
+ * HBM for XLG_OUT_DEVICE groups (a synchronous D2H copy: verification and tools, not
+ * the data path).  *out_len = complex samples the client produced. */
+int xlg_read_output(xlg_group *g, int64_t ticket, int client_id, void *dst, size_t cap, size_t *out_len);
+
 /* Pinned host memory for input blocks (queue/ingest buffers). */
 void *xlg_alloc_pinned(size_t bytes);
 void xlg_free_pinned(void *p);

@@ -47,7 +47,7 @@ REFERENCE_SYMBOLS = (
 )
 GROUP_SYMBOLS = [
     "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_remove_client", "xlg_client_count", "xlg_submit",
-    "xlg_wait", "xlg_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
+    "xlg_wait", "xlg_output", "xlg_read_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
     "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats",
 ]
 
@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     L.xlg_wait.restype = C.c_int
     L.xlg_output.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.xlg_output.restype = C.c_int
+    L.xlg_read_output.argtypes = [vp, C.c_int64, C.c_int, vp, sz, C.POINTER(sz)]
+    L.xlg_read_output.restype = C.c_int
     L.xlg_alloc_pinned.argtypes = [sz]
     L.xlg_alloc_pinned.restype = vp
     L.xlg_free_pinned.argtypes = [vp]
@@ -302,6 +304,17 @@ class Group:
         if n == 0:
             return np.zeros(0, dtype=np.complex64)
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(2 * n,)).copy().view(np.complex64)
+
+    def read_output(self, ticket: int, cid: int, q15: bool = False) -> np.ndarray:
+        """Copy of one client's output wherever it lives (HBM for XLG_OUT_DEVICE groups)."""
+        _, n = self.output_ptr(ticket, cid)
+        buf = np.zeros((n, 2), dtype=np.int16) if q15 else np.zeros(n, dtype=np.complex64)
+        got = C.c_size_t(0)
+        code = self._L.xlg_read_output(self._h, ticket, cid, buf.ctypes.data, n, C.byref(got))
+        if code != 0:
+            raise RuntimeError(f"xlg_read_output -> {code}")
+        assert got.value == n
+        return buf
 
     def wait_stream(self, cuda_stream: int) -> None:
         code = self._L.xlg_wait_stream(self._h, cuda_stream)

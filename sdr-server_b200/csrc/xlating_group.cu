@@ -15,10 +15,10 @@
  *   per slot (XLG_SLOTS in flight): raw input staging, BlkInfo, per-output
  *                    oscillator table, output arena (+ pinned host mirrors)
  *
- * Streams: s_in (H2D), s_ph (oscillator pre-pass chain), s_c / s_c2 (convert + FIR,
- * alternating by block), s_out (D2H); events order them per block so block b+1's
+ * Streams: s_in (H2D), s_ph (oscillator pre-pass chain), s_cs[0..n_cs) (convert + FIR,
+ * round-robin by block; 2 by default, XLATING_B200_CSTREAMS=1..4), s_out (D2H); events order them per block so block b+1's
  * copy and pre-pass overlap block b's FIR and consecutive FIRs overlap each other.
- * With XLG_SM_PARTITION s_ph lives in an 8-SM green context and s_c / s_c2 in the rest.
+ * With XLG_SM_PARTITION s_ph lives in an 8-SM green context and the compute streams in the rest.
  *
  * The reference's per-client dsp loop this replaces: src/dsp_worker.c:41-88 calling
  * src/xlating.c:384-414 -> :52-83 once per client per block.
@@ -162,7 +162,10 @@ struct xlg_group {
   uint32_t fs = 0;
   uint32_t max_input_len = 0;  // scalar elements
   uint32_t flags = 0;
-  cudaStream_t s_in = nullptr, s_ph = nullptr, s_c = nullptr, s_c2 = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_ph = nullptr, s_out = nullptr;
+  static constexpr int kMaxCs = 4;
+  cudaStream_t s_cs[kMaxCs] = {nullptr, nullptr, nullptr, nullptr};  // compute streams, round-robin by block
+  int n_cs = 2;
   SmPartition part;
 
   float2 *ring = nullptr;
@@ -243,8 +246,7 @@ static void slot_free(Slot &s) {
 static int drain(xlg_group *g) {
   CU_OK(cudaStreamSynchronize(g->s_in));
   CU_OK(cudaStreamSynchronize(g->s_ph));
-  CU_OK(cudaStreamSynchronize(g->s_c));
-  CU_OK(cudaStreamSynchronize(g->s_c2));
+  for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamSynchronize(g->s_cs[i]));
   CU_OK(cudaStreamSynchronize(g->s_out));
   return 0;
 }
@@ -740,15 +742,17 @@ static void partition_create(xlg_group *g, int device) {
   CUdevResource all, small, rest;
   unsigned int groups = 1;
   CUdevResourceDesc d_small = nullptr, d_rest = nullptr;
-  CUstream st_ph = nullptr, st_c = nullptr, st_c2 = nullptr;
+  CUstream st_ph = nullptr, st_c[xlg_group::kMaxCs] = {nullptr, nullptr, nullptr, nullptr};
   if (p_devget(&dev, device) != CUDA_SUCCESS || p_getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
       p_split(&small, &groups, &all, &rest, 0, 8) != CUDA_SUCCESS || groups != 1 ||
       p_desc(&d_small, &small, 1) != CUDA_SUCCESS || p_desc(&d_rest, &rest, 1) != CUDA_SUCCESS ||
       p_create(&g->part.small_ctx, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
       p_create(&g->part.big_ctx, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
       p_stream(&st_ph, g->part.small_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
-      p_stream(&st_c, g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
-      p_stream(&st_c2, g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+      p_stream(&st_c[0], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      p_stream(&st_c[1], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      p_stream(&st_c[2], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      p_stream(&st_c[3], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
     XL_LOG("could not create the SM partition (green contexts); continuing without it");
     cudaGetLastError();
     return;
@@ -756,8 +760,7 @@ static void partition_create(xlg_group *g, int device) {
   g->part.small_sms = (int)small.sm.smCount;
   g->part.big_sms = (int)rest.sm.smCount;
   g->s_ph = (cudaStream_t)st_ph;
-  g->s_c = (cudaStream_t)st_c;
-  g->s_c2 = (cudaStream_t)st_c2;
+  for (int i = 0; i < xlg_group::kMaxCs; i++) g->s_cs[i] = (cudaStream_t)st_c[i];
   g->part.ok = true;
 }
 
@@ -815,10 +818,9 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
       cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking) != cudaSuccess)
     return fail(-EIO);
   if (!g->part.ok) {
-    if (cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&g->s_c, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&g->s_c2, cudaStreamNonBlocking) != cudaSuccess)
-      return fail(-EIO);
+    if (cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
+    for (int i = 0; i < xlg_group::kMaxCs; i++)
+      if (cudaStreamCreateWithFlags(&g->s_cs[i], cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
   }
   const size_t raw_bytes = (size_t)max_input_len * 2;  // cs16 worst case
   for (Slot &s : g->slots) {
@@ -835,6 +837,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
   {
     const char *tv = getenv("XLATING_B200_TILE");
     if (tv != nullptr) g->tile_force = atoi(tv);
+    const char *cv = getenv("XLATING_B200_CSTREAMS");
+    if (cv != nullptr) g->n_cs = std::min(std::max(atoi(cv), 1), (int)xlg_group::kMaxCs);
     g->fir_sms = g->part.ok ? g->part.big_sms : prop.multiProcessorCount;
   }
   if (cudaFuncSetAttribute(fir_tile_cf32_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
@@ -863,8 +867,8 @@ extern "C" void xlg_destroy(xlg_group *g) {
   cudaSetDevice(g->device);
   if (g->s_in) cudaStreamSynchronize(g->s_in);
   if (g->s_ph) cudaStreamSynchronize(g->s_ph);
-  if (g->s_c) cudaStreamSynchronize(g->s_c);
-  if (g->s_c2) cudaStreamSynchronize(g->s_c2);
+  for (cudaStream_t st : g->s_cs)
+    if (st) cudaStreamSynchronize(st);
   if (g->s_out) cudaStreamSynchronize(g->s_out);
   if (g->d_trace != nullptr && g->trace_ctas > 0) {
     // timeline of the LAST tiled launch: mean cycles per CTA in each phase
@@ -922,8 +926,8 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_order) cudaFree(g->d_order);
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_ph) cudaStreamDestroy(g->s_ph);
-  if (g->s_c) cudaStreamDestroy(g->s_c);
-  if (g->s_c2) cudaStreamDestroy(g->s_c2);
+  for (cudaStream_t st : g->s_cs)
+    if (st) cudaStreamDestroy(st);
   if (g->s_out) cudaStreamDestroy(g->s_out);
   if (g->part.small_ctx || g->part.big_ctx) {
     pfn_cuGreenCtxDestroy p_destroy;
@@ -1091,7 +1095,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   // one block's FIR overlaps the head of the next (each block's launch alone
   // cannot fill 148 SMs evenly); per-kernel profiling keeps a single stream so
   // that event-timed durations are not inflated by the overlap
-  cudaStream_t cs = (g->profiling || (ticket & 1) == 0) ? g->s_c : g->s_c2;
+  cudaStream_t cs = g->profiling ? g->s_cs[0] : g->s_cs[ticket % g->n_cs];
 
   // ---- input staging ----
   const void *d_in = input;
@@ -1356,6 +1360,30 @@ extern "C" int xlg_output(xlg_group *g, int64_t ticket, int client_id, const voi
   return 0;
 }
 
+extern "C" int xlg_read_output(xlg_group *g, int64_t ticket, int client_id, void *dst, size_t cap, size_t *out_len) {
+  if (g == nullptr || dst == nullptr) return -EINVAL;
+  int rc = xlg_wait(g, ticket);
+  if (rc != 0) return rc;
+  const void *src = nullptr;
+  size_t n = 0;
+  rc = xlg_output(g, ticket, client_id, &src, &n);
+  if (rc != 0) return rc;
+  if (out_len) *out_len = n;
+  const HostOut &ho = g->ring_out[ticket % (int64_t)g->ring_out.size()];
+  const size_t bytes = std::min(n, cap) * (ho.q15 ? sizeof(short2) : sizeof(float2));
+  if (bytes == 0) return 0;
+  if (g->flags & XLG_OUT_DEVICE) {
+    cudaSetDevice(g->device);
+    CU_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    // the device arena may have been recycled while we copied
+    if (g->slots[ticket % XLG_SLOTS].ticket.load() != ticket) return -ESTALE;
+  } else {
+    memcpy(dst, src, bytes);
+    if (ho.ticket.load() != ticket) return -ESTALE;
+  }
+  return 0;
+}
+
 extern "C" void *xlg_alloc_pinned(size_t bytes) {
   void *p = nullptr;
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
@@ -1375,8 +1403,7 @@ extern "C" int xlg_wait_stream(xlg_group *g, void *cuda_stream) {
   cudaEvent_t ev;
   CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU_OK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-  CU_OK(cudaStreamWaitEvent(g->s_c, ev, 0));
-  CU_OK(cudaStreamWaitEvent(g->s_c2, ev, 0));
+  for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamWaitEvent(g->s_cs[i], ev, 0));
   CU_OK(cudaStreamWaitEvent(g->s_in, ev, 0));
   CU_OK(cudaEventDestroy(ev));
   return 0;
@@ -1386,10 +1413,10 @@ extern "C" int xlg_timer_start(xlg_group *g) {
   if (g == nullptr) return -EINVAL;
   cudaSetDevice(g->device);
   if (drain(g)) return -EIO;
-  CU_OK(cudaEventRecord(g->ev_t0, g->s_c));
+  CU_OK(cudaEventRecord(g->ev_t0, g->s_cs[0]));
   // every stream starts after t0
   CU_OK(cudaStreamWaitEvent(g->s_in, g->ev_t0, 0));
-  CU_OK(cudaStreamWaitEvent(g->s_c2, g->ev_t0, 0));
+  for (int i = 1; i < g->n_cs; i++) CU_OK(cudaStreamWaitEvent(g->s_cs[i], g->ev_t0, 0));
   CU_OK(cudaStreamWaitEvent(g->s_ph, g->ev_t0, 0));
   CU_OK(cudaStreamWaitEvent(g->s_out, g->ev_t0, 0));
   return 0;
@@ -1401,8 +1428,10 @@ extern "C" int xlg_timer_stop(xlg_group *g, float *elapsed_ms) {
   // s_out's last event already depends on the FIR of the last block; add the others
   cudaEvent_t ev;
   CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  cudaStream_t others[] = {g->s_in, g->s_ph, g->s_c, g->s_c2};
-  for (cudaStream_t st : others) {
+  cudaStream_t others[2 + xlg_group::kMaxCs] = {g->s_in, g->s_ph};
+  for (int i = 0; i < g->n_cs; i++) others[2 + i] = g->s_cs[i];
+  for (int oi = 0; oi < 2 + g->n_cs; oi++) {
+    cudaStream_t st = others[oi];
     CU_OK(cudaEventRecord(ev, st));
     CU_OK(cudaStreamWaitEvent(g->s_out, ev, 0));
   }

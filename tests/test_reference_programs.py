@@ -59,9 +59,6 @@ def test_reference_xlating_unit_test_fails_loudly_without_a_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run on a B200 is the "
-                                        "driver's; the same vectors with the same (int32)(x*10000) comparison pass "
-                                        "in tests/test_gpu_parity.py::test_fixture_*")
 def test_reference_xlating_unit_test_passes_on_the_gpu():
     """test/test_xlating.c:24-81, unmodified: full block, partial blocks with carried
     history and phase, too-short input; float path at 4 decimals, Q15 path exactly."""
@@ -162,7 +159,6 @@ def test_reference_dsp_workers_on_this_library_fail_loudly_without_a_gpu(tmp_pat
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first run on a B200 is the driver's")
 def test_reference_dsp_workers_on_this_library_match_the_reference(tmp_path):
     """The reference's own dsp_worker.c threads and queue.c queues, unmodified, calling into
     libxlating_b200.so: every client's output file equals the one the same threads write on

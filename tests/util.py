@@ -50,3 +50,24 @@ def assert_cf32_close(got, ref, what=""):
     bad = np.nonzero(d > bound)[0]
     assert bad.size == 0, f"{what}: {bad.size} outputs beyond element-wise bound, first k={bad[0]}"
     return float(d.max() / scale)
+
+
+def oracle_stream(oracles, fmt, blocks, keep=None, workers=None, renorm=True):
+    """Run every oracle filter over the whole block sequence (in order: the filters
+    carry history and phase) on a thread pool -- ctypes releases the GIL while the C
+    oracle runs.  Returns out[client][block] for the block indices in `keep` (all
+    blocks when None); other entries are None."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    keep = set(range(len(blocks))) if keep is None else set(keep)
+    workers = workers or min(len(oracles), max(1, (os.cpu_count() or 2) - 1), 64)
+
+    def run(o):
+        res = []
+        for b, x in enumerate(blocks):
+            y = o.process_cf32(fmt, x, renorm=renorm)
+            res.append(y if b in keep else None)
+        return res
+
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(run, oracles))

@@ -1,5 +1,5 @@
 /*
- * csrc/loopbench.cu -- inner-loop ceiling of the tiled FIR kernels.
+ * tools/loopbench.cu -- inner-loop ceiling of the tiled FIR kernels.
  *
  * Runs only the shared-memory-load + FMA body of fir_tile_cf32_kernel (scalar FFMA,
  * 4 outputs x 8 clients per thread) and fir_tile2_cf32_kernel (packed FFMA2,

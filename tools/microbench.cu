@@ -1,5 +1,5 @@
 /*
- * csrc/microbench.cu -- FP32 pipe micro-benchmarks for the roofline denominators.
+ * tools/microbench.cu -- FP32 pipe micro-benchmarks for the roofline denominators.
  *
  * MEASURED_PEAKS.json holds an HBM copy figure and a bf16 tensor figure, but the
  * xlating FIR is bound by the FP32 FMA pipe, so the peak it
