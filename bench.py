@@ -217,36 +217,66 @@ CPU_VARIANTS = [  # (binary suffix, gcc flags on top of -O3 -DNDEBUG -ffast-math
 ]
 
 
-def cpu_arm(wl, blocks, warmup_blocks, variants=("avx", "v3", "v4", "release"), seconds_cap=40.0):
-    """Runs oracle/_ref/ref_cpu_bench_<variant> (the reference compiled from its own sources)
-    for every flag set this CPU supports and quotes the FASTEST (BASELINE.md section 3:
-    quote the best case so that the comparison is not flattering)."""
+CPU_MODES = [  # (label, extra argv after <native|optimized>): max_threads, pin|nopin, main|local
+    ("pinned, one thread per logical CPU, filters created by the main thread (the reference's acceptor-thread model)",
+     ["0", "pin", "main"]),
+    ("unpinned, one thread per logical CPU, filters created by the main thread", ["0", "nopin", "main"]),
+    ("pinned, one thread per logical CPU, each thread creates its own filters (NUMA-local working buffers)",
+     ["0", "pin", "local"]),
+    ("pinned, one thread per PHYSICAL core, each thread creates its own filters", ["half", "pin", "local"]),
+]
+
+
+def cpu_arm(wl, blocks, warmup_blocks, variants=("avx", "v3", "v4", "release"), seconds_cap=60.0):
+    """Runs oracle/_ref/ref_cpu_bench_<variant> (the reference compiled from its own sources;
+    pinned thread-per-client in C).  The threading mode is chosen by a
+    short probe of four modes with the AVX build, then every flag set this CPU supports is
+    timed in that mode and the FASTEST is quoted, so that the comparison is not flattering."""
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
     flags = cpu_flags()
     plan = "\n".join(f"{p['decimation']} {p['cutoff']} {p['tw']} {p['center']}" for p in wl["plan"]) + "\n"
-    runs = {}
+    ncpu = len(os.sched_getaffinity(0))
+
+    def run(name, nblocks, nwarm, mode):
+        exe = os.path.join(ref_dir, f"ref_cpu_bench_{name}")
+        extra = [str(max(1, ncpu // 2)) if a == "half" else a for a in mode]
+        r = subprocess.run([exe, str(wl["fs"]), wl["fmt"], str(wl["block_elems"]), str(nblocks), str(nwarm),
+                            "optimized"] + extra, input=plan, capture_output=True, text=True, timeout=600)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+
     t_start = time.perf_counter()
+    probe_exe = next((n for n in ("avx", "release") if os.path.exists(os.path.join(ref_dir, f"ref_cpu_bench_{n}"))
+                      and (n == "release" or {"avx2", "fma"} <= flags)), None)
+    if probe_exe is None:
+        raise RuntimeError("oracle/_ref/ref_cpu_bench_* not built (oracle/_ref is built where /root/reference exists)")
+    probes = {}
+    for label, mode in CPU_MODES:
+        try:
+            probes[label] = run(probe_exe, 48, 8, mode)["input_msps"]
+        except Exception as ex:  # noqa: BLE001
+            probes[label] = repr(ex)
+    good = {k: v for k, v in probes.items() if isinstance(v, float)}
+    if not good:
+        raise RuntimeError(f"no reference CPU run succeeded: {probes}")
+    best_label = max(good, key=good.get)
+    best_mode = dict(CPU_MODES)[best_label]
+    runs = {}
     for name, gcc, need in CPU_VARIANTS:
         if name not in variants:
             continue
-        exe = os.path.join(ref_dir, f"ref_cpu_bench_{name}")
-        if not os.path.exists(exe):
-            runs[name] = {"skipped": "not built (oracle/_ref is built where /root/reference exists)"}
-            continue
-        if not need <= flags:
+        if not os.path.exists(os.path.join(ref_dir, f"ref_cpu_bench_{name}")):
+            runs[name] = {"skipped": "not built"}
+        elif not need <= flags:
             runs[name] = {"skipped": f"this CPU lacks {sorted(need - flags)}"}
-            continue
-        if runs and time.perf_counter() - t_start > seconds_cap:
+        elif runs and time.perf_counter() - t_start > seconds_cap:
             runs[name] = {"skipped": "time budget of the CPU leg spent"}
-            continue
-        try:
-            r = subprocess.run([exe, str(wl["fs"]), wl["fmt"], str(wl["block_elems"]), str(blocks), str(warmup_blocks),
-                                "optimized"], input=plan, capture_output=True, text=True, timeout=600)
-            d = json.loads(r.stdout.strip().splitlines()[-1])
-            d["gcc_flags"] = "-O3 -DNDEBUG -ffast-math " + gcc
-            runs[name] = d
-        except Exception as ex:  # noqa: BLE001
-            runs[name] = {"error": repr(ex)}
+        else:
+            try:
+                d = run(name, blocks, warmup_blocks, best_mode)
+                d["gcc_flags"] = "-O3 -DNDEBUG -ffast-math " + gcc
+                runs[name] = d
+            except Exception as ex:  # noqa: BLE001
+                runs[name] = {"error": repr(ex)}
     ok = {k: v for k, v in runs.items() if "input_msps" in v}
     if not ok:
         raise RuntimeError(f"no reference CPU binary could run: {runs}")
@@ -254,12 +284,12 @@ def cpu_arm(wl, blocks, warmup_blocks, variants=("avx", "v3", "v4", "release"), 
     b = ok[best]
     return {"value": b["input_msps"], "unit": "MS/s", "cores": b["threads"], "kind": "reference",
             "sample": f"{b['blocks']} blocks of {BLOCK_BYTES} B through all {b['clients']} clients after "
-                      f"{b['warmup_blocks']} warm-up blocks, {b['threads']} pinned pthreads (thread-per-client, "
-                      f"src/dsp_worker.c:41-88 without I/O and queue memcpy), oracle/_ref/ref_cpu_bench_{best} = "
+                      f"{b['warmup_blocks']} warm-up blocks; {b['threads']} threads: {best_label}; thread-per-client "
+                      f"(src/dsp_worker.c:41-88 without I/O and queue memcpy); oracle/_ref/ref_cpu_bench_{best} = "
                       f"unmodified reference sources, gcc {b['gcc_flags']}, process_optimized_* "
                       f"(SIMD_STATUS={b['simd_status']}), wall {b['seconds']:.2f} s",
-            "client_msps": b["client_msps"], "best_variant": best, "cpu_model": cpu_model(),
-            "nproc": os.cpu_count(),
+            "client_msps": b["client_msps"], "best_variant": best, "cpu_model": cpu_model(), "nproc": os.cpu_count(),
+            "threading_probe_msps": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in probes.items()},
             "variants": {k: (round(v["input_msps"], 3) if "input_msps" in v else v) for k, v in runs.items()}}
 
 
@@ -535,7 +565,7 @@ def run_stream_leg(pkg, wl, args, rank, world, local_rank, steps, warmup, partit
         def run_e2e(k):
             pend = []
             for s in range(k):
-                pend.append(g2.submit_ptr(fmt_code, pins[s % n_pin].ptr, wl["block_elems"], 0))
+                pend.append(g2.submit_ptr(fmt_code, pins[s % n_pin].ptr, wl["block_elems"], pkg.XLG_INPUT_KEEP))  # 8 rotating pinned blocks
                 if len(pend) >= pkg.XLG_SLOTS - 1:
                     tk = pend.pop(0)
                     g2.wait(tk)

@@ -51,6 +51,11 @@ enum { XLG_FMT_CU8 = 0, XLG_FMT_CS8 = 1, XLG_FMT_CS16 = 2 };
 /* xlg_submit flags */
 #define XLG_INPUT_DEVICE 0x100u /* `input` is a device pointer on the group's GPU (already staged) */
 #define XLG_PATH_Q15 0x200u     /* Q15 integer path (src/xlating.c:92-140) instead of cf32 */
+#define XLG_INPUT_KEEP 0x400u   /* `input` is page-locked host memory that the caller leaves untouched until
+                                   xlg_input_consumed(ticket) (or xlg_wait) returns: xlg_submit then returns
+                                   without waiting for the H2D copy.  Without this flag a page-locked input may
+                                   be reused as soon as xlg_submit returns, exactly like a pageable one (which
+                                   is staged through the group's own pinned buffer with a memcpy). */
 
 /* depth of the device pipeline (blocks in flight).  Outputs of ticket t stay valid
  * until ticket t + XLG_SLOTS (or t + host_ring, see xlg_create_ex) is submitted;
@@ -81,6 +86,9 @@ int xlg_client_count(const xlg_group *g);
  * ticket (0,1,2,...) immediately; work proceeds asynchronously.  Blocks when
  * XLG_SLOTS tickets are already in flight and the oldest has not completed. */
 int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t input_len, uint32_t flags);
+
+/* Block until the H2D copy of ticket's input block has completed (XLG_INPUT_KEEP submits). */
+int xlg_input_consumed(xlg_group *g, int64_t ticket);
 
 /* Block until ticket's outputs are complete (in pinned host memory, or in HBM
  * with XLG_OUT_DEVICE). */

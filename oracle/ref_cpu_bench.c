@@ -9,7 +9,11 @@
  * CLOCK_MONOTONIC wall time, not clock().
  *
  * usage: ref_cpu_bench <fs> <cu8|cs8|cs16> <block_elems> <blocks> <warmup_blocks>
- *                      <native|optimized> [max_threads]   < plan
+ *                      <native|optimized> [max_threads [pin|nopin [main|local]]]   < plan
+ *   pin|nopin   one thread per allowed CPU, pinned (default) / left to the scheduler
+ *   main|local  filters created by the main thread, as the reference's acceptor thread
+ *               does (src/tcp_server.c:327; default) / by the thread that runs them, which
+ *               puts their working buffers on that thread's NUMA node (favours the CPU)
  * plan (stdin): one client per line "decimation cutoff transition_width center_offset"
  *
  * Prints one JSON line.  bench.py --impl reference and the cpu_baseline leg run it.
@@ -34,9 +38,25 @@ typedef struct {
   xlating *filter;
 } client_t;
 
-static client_t *g_clients;
-static int g_n_clients, g_n_threads, g_blocks, g_warmup, g_fmt, g_optimized;
 static size_t g_block_elems;
+static size_t g_block_elems_for_create(void) { return g_block_elems; }
+static client_t *g_clients;
+static int g_n_clients, g_n_threads, g_blocks, g_warmup, g_fmt, g_optimized, g_local;
+static uint32_t g_fs;
+static size_t g_taps_min = (size_t)-1, g_taps_max = 0;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int create_client(client_t *c) {
+  float *taps = NULL;
+  size_t len = 0;
+  if (create_low_pass_filter(1.0f, g_fs, c->cutoff, c->tw, &taps, &len) != 0) return 1;
+  pthread_mutex_lock(&g_mu);
+  if (len < g_taps_min) g_taps_min = len;
+  if (len > g_taps_max) g_taps_max = len;
+  pthread_mutex_unlock(&g_mu);
+  return create_frequency_xlating_filter(c->decimation, taps, len, c->center, g_fs, (uint32_t)g_block_elems_for_create(),
+                                         &c->filter);
+}
 static uint8_t *g_data[8];
 static pthread_barrier_t g_barrier;
 static struct timespec g_t0, g_t1;
@@ -58,6 +78,9 @@ static void process(client_t *c, const uint8_t *blk, size_t *n_out) {
 static void *worker(void *arg) {
   const int tid = (int)(intptr_t)arg;
   uint64_t outputs = 0;
+  if (g_local)
+    for (int c = tid; c < g_n_clients; c += g_n_threads)
+      if (create_client(&g_clients[c]) != 0) exit(1);
   for (int b = 0; b < g_warmup + g_blocks; b++) {
     if (b == g_warmup) {
       pthread_barrier_wait(&g_barrier);
@@ -81,13 +104,15 @@ int main(int argc, char **argv) {
     fprintf(stderr, "usage: %s fs fmt block_elems blocks warmup native|optimized [max_threads] < plan\n", argv[0]);
     return 2;
   }
-  const uint32_t fs = (uint32_t)strtoul(argv[1], NULL, 10);
+  g_fs = (uint32_t)strtoul(argv[1], NULL, 10);
   g_fmt = strcmp(argv[2], "cu8") == 0 ? 0 : (strcmp(argv[2], "cs8") == 0 ? 1 : 2);
   g_block_elems = (size_t)strtoul(argv[3], NULL, 10);
   g_blocks = atoi(argv[4]);
   g_warmup = atoi(argv[5]);
   g_optimized = strcmp(argv[6], "optimized") == 0;
   int max_threads = argc > 7 ? atoi(argv[7]) : 0;
+  const int pin = !(argc > 8 && strcmp(argv[8], "nopin") == 0);
+  g_local = argc > 9 && strcmp(argv[9], "local") == 0;
 
   int cap = 64;
   g_clients = (client_t *)calloc((size_t)cap, sizeof(client_t));
@@ -105,17 +130,9 @@ int main(int argc, char **argv) {
     fprintf(stderr, "empty plan\n");
     return 2;
   }
-  size_t taps_min = (size_t)-1, taps_max = 0;
-  for (int i = 0; i < g_n_clients; i++) {
-    float *taps = NULL;
-    size_t len = 0;
-    if (create_low_pass_filter(1.0f, fs, g_clients[i].cutoff, g_clients[i].tw, &taps, &len) != 0) return 1;
-    if (len < taps_min) taps_min = len;
-    if (len > taps_max) taps_max = len;
-    if (create_frequency_xlating_filter(g_clients[i].decimation, taps, len, g_clients[i].center, fs,
-                                        (uint32_t)g_block_elems, &g_clients[i].filter) != 0)
-      return 1;
-  }
+  if (!g_local)
+    for (int i = 0; i < g_n_clients; i++)
+      if (create_client(&g_clients[i]) != 0) return 1;
   /* synthetic blocks: xorshift64 bytes (cs16: 14-bit samples), the same in every build */
   const size_t bytes = g_block_elems * (g_fmt == 2 ? 2 : 1);
   uint64_t s = 0x9E3779B97F4A7C15ull;
@@ -149,7 +166,7 @@ int main(int argc, char **argv) {
     cpu_set_t one;
     CPU_ZERO(&one);
     CPU_SET(cpus[t % n_cpus], &one);
-    pthread_attr_setaffinity_np(&attr, sizeof(one), &one);
+    if (pin) pthread_attr_setaffinity_np(&attr, sizeof(one), &one);
     pthread_create(&th[t], &attr, worker, (void *)(intptr_t)t);
     pthread_attr_destroy(&attr);
   }
@@ -159,11 +176,11 @@ int main(int argc, char **argv) {
   for (int t = 0; t < 1024; t++) outputs += g_outputs[t];
   const double in_samples = (double)g_blocks * (double)(g_block_elems / 2);
   printf("{\"bench\": \"ref_cpu_bench\", \"simd_status\": \"%s\", \"variant\": \"%s\", \"clients\": %d, \"threads\": %d, "
-         "\"cpus_allowed\": %d, \"pinned\": true, \"blocks\": %d, \"warmup_blocks\": %d, \"block_elems\": %zu, "
+         "\"cpus_allowed\": %d, \"pinned\": %s, \"filters_created_by\": \"%s\", \"blocks\": %d, \"warmup_blocks\": %d, \"block_elems\": %zu, "
          "\"taps_min\": %zu, \"taps_max\": %zu, \"seconds\": %.6f, \"input_msps\": %.4f, \"client_msps\": %.2f, "
          "\"outputs\": %llu}\n",
-         SIMD_STATUS, g_optimized ? "optimized" : "native", g_n_clients, g_n_threads, n_cpus, g_blocks, g_warmup,
-         g_block_elems, taps_min, taps_max, dt, in_samples / dt / 1e6, in_samples / dt / 1e6 * g_n_clients,
+         SIMD_STATUS, g_optimized ? "optimized" : "native", g_n_clients, g_n_threads, n_cpus, pin ? "true" : "false",
+         g_local ? "the thread that runs them" : "the main thread", g_blocks, g_warmup, g_block_elems, g_taps_min, g_taps_max, dt, in_samples / dt / 1e6, in_samples / dt / 1e6 * g_n_clients,
          (unsigned long long)outputs);
   for (int i = 0; i < g_n_clients; i++) destroy_xlating(g_clients[i].filter);
   return 0;

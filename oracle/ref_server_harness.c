@@ -9,8 +9,13 @@
  *                                 sdr_callback (src/tcp_server.c:257-271)
  *   dsp_worker_destroy()          drains the client's queue, joins its dsp thread
  *
- * oracle/Makefile links it twice: with the reference's src/xlating.c + src/lpf.c
- * (server_harness_ref) and with libxlating_b200.so instead (server_harness_b200).
+ * oracle/build_ref.sh links it with the reference's src/xlating.c + src/lpf.c
+ * (server_harness_ref), with libxlating_b200.so instead (server_harness_b200; _pinnedq =
+ * with sdr-server_b200/host/queue_pinned.c in place of src/queue.c), and -- compiled with
+ * -DHARNESS_CUDA_CF32 against the reference tree PATCHED with integration/cuda_cf32.patch --
+ * in the patch's cpu_optimization = CUDA_CF32 mode (server_harness_patched_b200): one
+ * xlg_submit per block, an 8-byte ticket per client, exactly what the patched
+ * sdr_callback does (src/tcp_server.c:257-271 after the patch).
  * Both write <base_path>/<id>.cf32 exactly as the server does, so the two can be
  * compared file by file, and both print (last line of stdout) the wall-clock input rate
  * they sustained.
@@ -40,7 +45,11 @@ int main(int argc, char **argv) {
   const int n_blocks = atoi(argv[2]);
   struct server_config server;
   memset(&server, 0, sizeof(server));
+#ifdef HARNESS_CUDA_CF32
+  server.optimization = CUDA_CF32; /* integration/cuda_cf32.patch */
+#else
   server.optimization = OPTIMIZED_CF32; /* the shipped default, src/config.c:252-264 */
+#endif
   server.sdr_type = SDR_TYPE_RTL;
   server.band_sampling_rate = 2016000;
   if (argc > 5 && strcmp(argv[5], "airspy") == 0) {
@@ -79,6 +88,18 @@ int main(int argc, char **argv) {
     fclose(f);
   }
 
+#ifdef HARNESS_CUDA_CF32
+  /* what the patched handle_new_client does for the first client (src/tcp_server.c after the patch) */
+  xlg_group *group = NULL;
+  {
+    const uint32_t max_elements = server.sdr_type == SDR_TYPE_AIRSPY ? server.buffer_size / 2 : server.buffer_size;
+    const int code = xlg_create_ex(0, server.band_sampling_rate, max_elements, 0, (uint32_t)server.queue_size, &group);
+    if (code != 0) {
+      fprintf(stderr, "xlg_create_ex -> %d\n", code);
+      return 1;
+    }
+  }
+#endif
   const uint32_t band_freq = 100000000u;
   const uint32_t fs = server.band_sampling_rate;
   client_config *configs = (client_config *)calloc((size_t)n_clients, sizeof(client_config));
@@ -99,14 +120,35 @@ int main(int argc, char **argv) {
       fprintf(stderr, "dsp_worker_start(client %d) -> %d\n", c, code);
       return 1;
     }
+#ifdef HARNESS_CUDA_CF32
+    if (dsp_worker_attach_group(workers[c], group) != 0) {
+      fprintf(stderr, "dsp_worker_attach_group(client %d) failed\n", c);
+      return 1;
+    }
+#endif
   }
 
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
+#ifdef HARNESS_CUDA_CF32
+  const int fmt = server.sdr_type == SDR_TYPE_AIRSPY ? XLG_FMT_CS16 : (server.sdr_type == SDR_TYPE_HACKRF ? XLG_FMT_CS8 : XLG_FMT_CU8);
+  const size_t elements = server.sdr_type == SDR_TYPE_AIRSPY ? server.buffer_size / 2 : server.buffer_size;
+  for (int b = 0; b < n_blocks; b++) { /* the patched sdr_callback: ONE submit, a ticket per client */
+    const int64_t ticket = xlg_submit(group, fmt, blocks + (size_t)b * server.buffer_size, elements, 0);
+    if (ticket < 0) {
+      fprintf(stderr, "xlg_submit -> %lld\n", (long long)ticket);
+      return 1;
+    }
+    for (int c = 0; c < n_clients; c++) dsp_worker_process_ticket(ticket, workers[c]);
+  }
+  for (int c = 0; c < n_clients; c++) dsp_worker_destroy(workers[c]); /* drain + join */
+  xlg_destroy(group);
+#else
   for (int b = 0; b < n_blocks; b++) /* sdr_callback: the same block to every client */
     for (int c = 0; c < n_clients; c++)
       dsp_worker_process(blocks + (size_t)b * server.buffer_size, server.buffer_size, workers[c]);
   for (int c = 0; c < n_clients; c++) dsp_worker_destroy(workers[c]); /* drain + join */
+#endif
   clock_gettime(CLOCK_MONOTONIC, &t1);
   const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   const double samples = (double)n_blocks * server.buffer_size / (server.sdr_type == SDR_TYPE_AIRSPY ? 4 : 2);

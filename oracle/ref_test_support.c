@@ -56,3 +56,43 @@ void assert_cs16(const int16_t expected[], size_t expected_size, int16_t *actual
   TEST_ASSERT_EQUAL_INT(expected_size, actual_size);
   for (size_t k = 0; k < 2 * expected_size; k++) TEST_ASSERT_EQUAL_INT(expected[k], actual[k]);
 }
+
+/* ---- helpers of the server test (test/utils.c:198-252): the file a client's dsp
+ * thread wrote, plain or gzip'd, must hold the expected samples ---- */
+#include <stdio.h>
+#include <zlib.h>
+
+#include "config.h"
+
+void assert_file(struct server_config *config, int id, const float expected[], size_t expected_size) {
+  char path[4096];
+  snprintf(path, sizeof(path), "%s/%d.cf32", config->base_path, id);
+  FILE *f = fopen(path, "rb");
+  TEST_ASSERT_NOT_NULL(f);
+  float complex *samples = (float complex *)malloc(sizeof(float complex) * (expected_size + 1));
+  TEST_ASSERT_NOT_NULL(samples);
+  const size_t got = fread(samples, sizeof(float complex), expected_size + 1, f);
+  fclose(f);
+  assert_cf32(expected, expected_size, samples, got);
+  free(samples);
+}
+
+void assert_gzfile(struct server_config *config, int id, const float expected[], size_t expected_size) {
+  char path[4096];
+  snprintf(path, sizeof(path), "%s/%d.cf32.gz", config->base_path, id);
+  gzFile f = gzopen(path, "rb");
+  TEST_ASSERT_NOT_NULL(f);
+  float complex *samples = (float complex *)malloc(sizeof(float complex) * expected_size);
+  TEST_ASSERT_NOT_NULL(samples);
+  size_t have = 0;
+  const size_t want = sizeof(float complex) * expected_size;
+  while (have < want) {
+    const int n = gzread(f, (char *)samples + have, (unsigned)(want - have));
+    if (n <= 0) break;
+    have += (size_t)n;
+  }
+  gzclose(f);
+  TEST_ASSERT_EQUAL_INT(want, have);
+  assert_cf32(expected, expected_size, samples, expected_size);
+  free(samples);
+}

@@ -38,6 +38,7 @@ XLG_FORCE_GENERIC = 0x4
 XLG_SM_PARTITION = 0x10
 XLG_INPUT_DEVICE = 0x100
 XLG_PATH_Q15 = 0x200
+XLG_INPUT_KEEP = 0x400
 XLG_SLOTS = 4
 
 # every symbol the headers declare (checked by tests/test_abi.py)
@@ -47,7 +48,7 @@ REFERENCE_SYMBOLS = (
 )
 GROUP_SYMBOLS = [
     "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_remove_client", "xlg_client_count", "xlg_submit",
-    "xlg_wait", "xlg_output", "xlg_read_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
+    "xlg_wait", "xlg_input_consumed", "xlg_output", "xlg_read_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
     "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats",
 ]
 
@@ -109,6 +110,8 @@ def lib() -> C.CDLL:
     L.xlg_submit.restype = C.c_int64
     L.xlg_wait.argtypes = [vp, C.c_int64]
     L.xlg_wait.restype = C.c_int
+    L.xlg_input_consumed.argtypes = [vp, C.c_int64]
+    L.xlg_input_consumed.restype = C.c_int
     L.xlg_output.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.xlg_output.restype = C.c_int
     L.xlg_read_output.argtypes = [vp, C.c_int64, C.c_int, vp, sz, C.POINTER(sz)]
@@ -412,7 +415,7 @@ class XlClientConfig(C.Structure):
 class XlStreamConfig(C.Structure):
     _fields_ = [("sdr_type", C.c_int), ("band_sampling_rate", C.c_uint32), ("buffer_size", C.c_uint32),
                 ("queue_size", C.c_int), ("lpf_cutoff_rate", C.c_int), ("base_path", C.c_char_p),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("use_gzip", C.c_int)]
 
 
 _host = None
@@ -450,7 +453,7 @@ def host_lib() -> C.CDLL:
     H.xl_stream_push.argtypes = [vp, vp, C.c_uint32]
     H.xl_stream_push.restype = C.c_int
     H.xl_stream_flush.argtypes = [vp]
-    H.xl_stream_flush.restype = None
+    H.xl_stream_flush.restype = C.c_int
     H.xl_stream_destroy.argtypes = [vp]
     H.xl_stream_destroy.restype = None
     H.xl_stream_client_count.argtypes = [vp]

@@ -870,6 +870,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
   for (cudaStream_t st : g->s_cs)
     if (st) cudaStreamSynchronize(st);
   if (g->s_out) cudaStreamSynchronize(g->s_out);
+  if (g->d_trace != nullptr && g->trace_ctas <= 0) cudaFree(g->d_trace);
   if (g->d_trace != nullptr && g->trace_ctas > 0) {
     // timeline of the LAST tiled launch: mean cycles per CTA in each phase
     std::vector<long long> t((size_t)4 * g->trace_ctas);
@@ -1115,6 +1116,10 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     CU_OK(cudaMemcpyAsync(s.d_raw, src, bytes, cudaMemcpyHostToDevice, g->s_in));
     CU_OK(cudaEventRecord(s.ev_h2d, g->s_in));
     CU_OK(cudaStreamWaitEvent(cs, s.ev_h2d, 0));
+    // caller-owned pinned memory is read by the copy engine AFTER this call returns: unless
+    // the caller promised to leave it alone (XLG_INPUT_KEEP), wait for the copy (a 256 KiB
+    // block is ~10 us) so that the buffer may be reused at once, like a pageable one
+    if (pinned && !(flags & XLG_INPUT_KEEP)) CU_OK(cudaEventSynchronize(s.ev_h2d));
     d_in = s.d_raw;
   }
 
@@ -1379,8 +1384,20 @@ extern "C" int xlg_read_output(xlg_group *g, int64_t ticket, int client_id, void
     if (g->slots[ticket % XLG_SLOTS].ticket.load() != ticket) return -ESTALE;
   } else {
     memcpy(dst, src, bytes);
+    // seqlock-style validation: xlg_submit marks the entry (ticket = -1) BEFORE it enqueues the
+    // copy that overwrites it, so an unchanged ticket after our reads means they saw this ticket's data
+    std::atomic_thread_fence(std::memory_order_acquire);
     if (ho.ticket.load() != ticket) return -ESTALE;
   }
+  return 0;
+}
+
+extern "C" int xlg_input_consumed(xlg_group *g, int64_t ticket) {
+  if (g == nullptr || ticket < 0 || ticket >= g->next_ticket.load()) return -EINVAL;
+  Slot &s = g->slots[ticket % XLG_SLOTS];
+  if (s.ticket.load() != ticket) return 0;  // the slot serves a later ticket: this one's copy finished long ago
+  cudaSetDevice(g->device);
+  CU_OK(cudaEventSynchronize(s.ev_h2d));
   return 0;
 }
 

@@ -37,9 +37,12 @@ typedef struct xl_dsp_worker xl_dsp_worker;
 
 /* Designs the client's low-pass (create_low_pass_filter(1.0, band_rate, rate/2,
  * rate/lpf_cutoff_rate), src/dsp_worker.c:98), attaches it to the group, opens
- * <base_path>/<id>.cf32 for file destinations (:126-144) and starts the thread. */
+ * <base_path>/<id>.cf32 -- or <id>.cf32.gz with use_gzip -- for file destinations
+ * (:126-144) and starts the thread.  max_block_elements sizes the client's private
+ * output buffer (largest block, in scalar elements). */
 int xl_dsp_worker_start(const xl_client_config *config, xlg_group *group, uint32_t band_sampling_rate,
-                        int lpf_cutoff_rate, int queue_size, const char *base_path, xl_dsp_worker **worker);
+                        uint32_t max_block_elements, int lpf_cutoff_rate, int queue_size, const char *base_path,
+                        int use_gzip, xl_dsp_worker **worker);
 
 /* called by the ingest side for every submitted block (dsp_worker_process, :202-204) */
 void xl_dsp_worker_post(xl_dsp_worker *worker, int64_t ticket);
@@ -49,6 +52,8 @@ void xl_dsp_worker_destroy(xl_dsp_worker *worker);
 
 uint64_t xl_dsp_worker_blocks_written(xl_dsp_worker *worker);
 uint64_t xl_dsp_worker_blocks_lost(xl_dsp_worker *worker);
+uint64_t xl_dsp_worker_blocks_failed(xl_dsp_worker *worker);  /* write errors (socket closed, disk full) */
+uint64_t xl_dsp_worker_queue_overruns(xl_dsp_worker *worker); /* tickets overwritten in a full queue */
 
 #ifdef __cplusplus
 }

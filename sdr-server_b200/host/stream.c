@@ -63,8 +63,10 @@ int xl_stream_add_client(xl_stream *s, const xl_client_config *client) {
     return -ENOMEM;
   }
   pthread_mutex_lock(&s->mutex);
-  int code = xl_dsp_worker_start(client, s->group, s->config.band_sampling_rate, s->config.lpf_cutoff_rate,
-                                 s->config.queue_size, s->config.base_path, &node->worker);
+  const uint32_t max_elems = s->config.sdr_type == XLG_FMT_CS16 ? s->config.buffer_size / (uint32_t)sizeof(int16_t)
+                                                                : s->config.buffer_size;
+  int code = xl_dsp_worker_start(client, s->group, s->config.band_sampling_rate, max_elems, s->config.lpf_cutoff_rate,
+                                 s->config.queue_size, s->config.base_path, s->config.use_gzip, &node->worker);
   if (code == 0) {
     node->id = client->id;
     node->next = s->clients;
@@ -120,21 +122,25 @@ int xl_stream_push(xl_stream *s, const uint8_t *buf, uint32_t buf_len) {
   return 0;
 }
 
-void xl_stream_flush(xl_stream *s) {
-  for (;;) {
+int xl_stream_flush(xl_stream *s) {
+  for (int spins = 0; spins < 150000; spins++) { /* 30 s */
     int pending = 0;
     pthread_mutex_lock(&s->mutex);
     for (struct client_node *n = s->clients; n != NULL; n = n->next) {
-      if (xl_dsp_worker_blocks_written(n->worker) + xl_dsp_worker_blocks_lost(n->worker) < n->posted) {
+      const uint64_t accounted = xl_dsp_worker_blocks_written(n->worker) + xl_dsp_worker_blocks_lost(n->worker) +
+                                 xl_dsp_worker_blocks_failed(n->worker) + xl_dsp_worker_queue_overruns(n->worker);
+      if (accounted < n->posted) {
         pending = 1;
       }
     }
     pthread_mutex_unlock(&s->mutex);
     if (!pending) {
-      return;
+      return 0;
     }
     usleep(200);
   }
+  fprintf(stderr, "<3>xl_stream_flush: clients still busy after 30 s\n");
+  return -ETIMEDOUT;
 }
 
 int xl_stream_client_count(xl_stream *s) {

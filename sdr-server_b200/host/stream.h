@@ -26,6 +26,7 @@ typedef struct {
   int lpf_cutoff_rate;         /* default 5  (src/config.c:213) */
   const char *base_path;       /* file destinations */
   int device;                  /* CUDA device ordinal */
+  int use_gzip;                /* file destinations are <id>.cf32.gz (src/config.c:250, default true there) */
 } xl_stream_config;
 
 typedef struct xl_stream xl_stream;
@@ -36,8 +37,10 @@ int xl_stream_add_client(xl_stream *stream, const xl_client_config *client);
 int xl_stream_remove_client(xl_stream *stream, uint32_t client_id);
 /* sdr_callback: one submit for all clients, then an 8-byte ticket per client */
 int xl_stream_push(xl_stream *stream, const uint8_t *buf, uint32_t buf_len);
-/* wait until every posted block has been written by every client (tests, shutdown) */
-void xl_stream_flush(xl_stream *stream);
+/* wait until every posted block has been accounted for by every client -- written, lost
+ * (-ESTALE), failed to write, or overwritten in a full queue -- or 30 s have passed
+ * (tests, shutdown).  Returns 0, or -ETIMEDOUT. */
+int xl_stream_flush(xl_stream *stream);
 void xl_stream_destroy(xl_stream *stream);
 int xl_stream_client_count(xl_stream *stream);
 

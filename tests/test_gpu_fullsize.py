@@ -182,8 +182,13 @@ def test_batch_path_320_blocks_no_drift(pkg):
 
 
 def test_long_filter_split_k_margin_64_clients(pkg):
-    """configs[4] shape on 64 clients x 6 blocks: split-K changes the order of 15419 fp32
-    additions (121 segments), so the margin to 1e-5 is asserted, not just the bound."""
+    """configs[4] shape on 64 clients x 6 blocks.  Split-K changes the order of 15419 fp32
+    additions (121 segments of 128 taps), and at this length the reference's OWN sequential
+    fp32 sum carries ~sqrt(T) * 6e-8 = 7e-6 of rounding noise, so the distance to it is
+    close to the 1e-5 contract by nature (measured: 7.8e-6 worst over these 384
+    client-blocks).  Two assertions: the contract itself, and -- against an exact float64
+    evaluation of the same dot products -- that the GPU result is at least as close to the
+    exact value as the reference's own arithmetic is."""
     rng = np.random.default_rng(131)
     fs, max_in = 61440000, 131072
     taps = pkg.create_low_pass_filter(1.0, fs, 24000, 9600)
@@ -195,10 +200,30 @@ def test_long_filter_split_k_margin_64_clients(pkg):
     blocks = [rand_block(rng, "cs16", max_in) for _ in range(6)]
     refs = oracle_stream(oracles, "cs16", blocks)
     worst = 0.0
+    got = [[] for _ in ids]
     for b, x in enumerate(blocks):
         t = g.submit("cs16", x)
         g.wait(t)
-        worst = max(worst, check_all(g, t, ids, refs, b, "long"))
+        for i, cid in enumerate(ids):
+            y = g.output(t, cid)
+            got[i].append(y)
+            worst = max(worst, assert_cf32_close(y, refs[i][b], f"long: block {b} client {i}"))
     assert {g.client_info(c)[1] for c in ids} == {2}
-    assert worst < 5e-6, worst
+    assert worst < 1e-5, worst
+    print(f"split-K vs the reference's sequential fp32 sum: worst norm-wise distance {worst:.2e}")
+    # exact magnitudes: |y_k| = |sum_j xpad[k*D + j] * rev[j]| (the oscillator has modulus 1 to ~1e-7)
+    stream = np.concatenate(blocks).astype(np.float64).reshape(-1, 2) / 32768.0
+    xpad = np.concatenate([np.zeros(len(taps) - 1, dtype=np.complex128), stream[:, 0] + 1j * stream[:, 1]])
+    closer = 0
+    for i in (0, 21, 42, 63):
+        rev = oracles[i].rev_taps.astype(np.complex128)
+        y_gpu, y_ref = np.concatenate(got[i]), np.concatenate(refs[i])
+        exact = np.array([np.abs(np.dot(xpad[k * 1280:k * 1280 + len(rev)], rev)) for k in range(len(y_ref))])
+        scale = exact.max()
+        e_gpu = np.max(np.abs(np.abs(y_gpu.astype(np.complex128)) - exact)) / scale
+        e_ref = np.max(np.abs(np.abs(y_ref.astype(np.complex128)) - exact)) / scale
+        print(f"client {i}: |y| error vs float64  GPU {e_gpu:.2e}  reference arithmetic {e_ref:.2e}")
+        assert e_gpu < 1e-5
+        closer += e_gpu <= e_ref + 2e-7
+    assert closer == 4, "the split-K sum should be at least as close to exact math as the sequential fp32 sum"
     g.close()

@@ -36,10 +36,81 @@ def unity_summary(stdout):
     return tuple(int(g) for g in m.groups())
 
 
-@pytest.mark.parametrize("name,tests", [("test_xlating_ref", 3), ("test_lpf_ref", 4)])
+@pytest.mark.parametrize("name,tests", [("test_xlating_ref", 3), ("test_lpf_ref", 4), ("test_queue_ref", 3)])
 def test_reference_unit_tests_pass_on_the_reference_with_our_stand_in(name, tests):
     r = subprocess.run([ref_program(name)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and unity_summary(r.stdout) == (tests, 0, 0), r.stdout[-400:]
+
+
+def run_server_test(name, tmp_path, optimization=None, timeout=300):
+    """test/test_tcp_server.c reads ./tcp_server.config (copied next to the binaries by
+    oracle/build_ref.sh) and writes <TMPDIR>/<id>.cf32[.gz]."""
+    exe = ref_program(name)
+    env = dict(os.environ, TMPDIR=str(tmp_path))
+    if optimization:
+        env["XL_TEST_CPU_OPTIMIZATION"] = optimization
+    return subprocess.run([exe], cwd=os.path.dirname(exe), env=env, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("name", ["test_tcp_server_ref", "test_tcp_server_patched_ref"])
+def test_reference_server_test_passes_on_the_reference(name, tmp_path):
+    """The reference's whole server integration test (test/test_tcp_server.c, unmodified: 11
+    tests -- protocol errors, rtl-sdr / airspy+gzip / hackrf golden outputs through
+    tcp_server -> queue -> dsp_worker -> socket/file, band arbitration) with the reference's
+    real tcp_server.c, dsp_worker.c, queue.c, sdr_device.c and vendor-lib mocks; stand-ins
+    only for the vendor HEADERS, libconfig and libpng.  `_ref` proves the stand-ins;
+    `_patched_ref` is the tree with integration/cuda_cf32.patch applied, still in its CPU
+    mode: the patch must not change the reference's behaviour."""
+    r = run_server_test(name, tmp_path)
+    assert r.returncode == 0 and unity_summary(r.stdout) == (11, 0, 0), r.stdout[-800:]
+
+
+def test_pinned_queue_keeps_the_reference_queue_semantics():
+    """test/test_queue.c:23-59 (FIFO, overwrite-newest, drain-before-poison), unmodified, on
+    sdr-server_b200/host/queue_pinned.c built with malloc instead of cudaHostAlloc."""
+    r = subprocess.run([ref_program("test_queue_pageable")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and unity_summary(r.stdout) == (3, 0, 0), r.stdout[-400:]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="this is the no-GPU behaviour")
+def test_pinned_queue_fails_loudly_without_a_gpu():
+    r = subprocess.run([ref_program("test_queue_pinned")], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "Expected -12 Was 0" in r.stdout  # create_queue -> -ENOMEM
+    assert "<3>" in r.stderr
+
+
+@pytest.mark.gpu
+def test_pinned_queue_passes_the_reference_queue_test_on_the_gpu_box():
+    r = subprocess.run([ref_program("test_queue_pinned")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and unity_summary(r.stdout) == (3, 0, 0), r.stdout[-400:]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/xlating.h"), reason="needs /root/reference")
+def test_cuda_cf32_patch_applies_to_the_reference(tmp_path):
+    """integration/cuda_cf32.patch is a real patch: it applies cleanly to a copy of the
+    reference's src/ and touches exactly the files INTEGRATION.md names."""
+    import shutil
+    shutil.copytree("/root/reference/src", tmp_path / "src")
+    with open(os.path.join(ROOT, "integration", "cuda_cf32.patch")) as f:
+        r = subprocess.run(["patch", "-p1", "-d", str(tmp_path)], stdin=f, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    patched = sorted(line.split()[-1] for line in r.stdout.splitlines() if line.startswith("patching file"))
+    assert patched == ["src/config.c", "src/config.h", "src/dsp_worker.c", "src/dsp_worker.h", "src/tcp_server.c"]
+    assert "CUDA_CF32" in (tmp_path / "src" / "config.h").read_text()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,optimization", [("test_tcp_server_b200", None),
+                                               ("test_tcp_server_patched_b200", "CUDA_CF32")])
+def test_reference_server_test_passes_on_this_library(name, optimization, tmp_path):
+    """The same 11 tests with libxlating_b200.so in place of src/xlating.c + src/lpf.c:
+    `_b200` = the unmodified reference (per-filter drop-in ABI, one dsp thread per client);
+    `_patched_b200` with cpu_optimization = CUDA_CF32 = the patched sdr_callback submits each
+    block once to the batch ABI and the dsp threads wait for tickets."""
+    r = run_server_test(name, tmp_path, optimization)
+    assert r.returncode == 0 and unity_summary(r.stdout) == (11, 0, 0), r.stdout[-1200:] + r.stderr[-600:]
+    if optimization:
+        assert "cpu_optimization: 2" in r.stdout  # the stand-in really selected CUDA_CF32
 
 
 def test_reference_lpf_unit_test_passes_on_this_library():
@@ -156,6 +227,35 @@ def test_reference_dsp_workers_on_this_library_fail_loudly_without_a_gpu(tmp_pat
     r = run_harness("server_harness_b200", 2, 2, 4, tmp_path)
     assert r.returncode != 0
     assert "dsp_worker_start(client 0) -> -19" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("harness", ["server_harness_patched_b200", "server_harness_b200_pinnedq"])
+def test_reference_dsp_workers_variants_match_the_reference(harness, tmp_path):
+    """The reference's dsp threads (a) from the tree patched with integration/cuda_cf32.patch in
+    CUDA_CF32 mode -- ONE xlg_submit per block, an 8-byte ticket per client through the
+    reference's own queue -- and (b) unmodified but on the pinned-block queue
+    (host/queue_pinned.c): every client's file equals the one the unmodified reference
+    writes with its own xlating.c."""
+    import json
+
+    import numpy as np
+
+    from util import assert_cf32_close
+    clients, blocks = 32, 12
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "b200").mkdir()
+    a = run_harness("server_harness_ref", clients, blocks, 16, tmp_path / "ref")
+    b = run_harness(harness, clients, blocks, 16, tmp_path / "b200")
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr[-300:], b.stderr[-600:])
+    for c in range(clients):
+        want = np.fromfile(tmp_path / "ref" / f"{c}.cf32", dtype=np.complex64)
+        got = np.fromfile(tmp_path / "b200" / f"{c}.cf32", dtype=np.complex64)
+        assert_cf32_close(got, want, f"client {c}")
+    (tmp_path / "t").mkdir()
+    gpu = run_harness(harness, 256, 64, 64, tmp_path / "t")
+    assert gpu.returncode == 0, gpu.stderr[-600:]
+    print(harness, "256 clients:", json.loads(gpu.stdout.strip().splitlines()[-1]))
 
 
 @pytest.mark.gpu
