@@ -48,6 +48,9 @@ enum { XLG_FMT_CU8 = 0, XLG_FMT_CS8 = 1, XLG_FMT_CS16 = 2 };
 #define XLG_SM_PARTITION 0x10u /* reserve 8 SMs (CUDA green context) for the oscillator pre-pass so that it
                                   overlaps the FIR of the previous block without fighting it for issue slots;
                                   meant for throughput-bound deployments with many high-rate clients */
+#define XLG_TRACK_STATE 0x20u  /* keep every client's state after each ticket (history_offset, oscillator) readable
+                                  with the ticket's results: xlg_copy_output(..., state_after).  Used by the
+                                  per-filter drop-in engine, which moves filters in and out of a group. */
 /* xlg_submit flags */
 #define XLG_INPUT_DEVICE 0x100u /* `input` is a device pointer on the group's GPU (already staged) */
 #define XLG_PATH_Q15 0x200u     /* Q15 integer path (src/xlating.c:92-140) instead of cf32 */
@@ -79,6 +82,18 @@ void xlg_destroy(xlg_group *g);
  * non-negative handle, stable until removed. */
 int xlg_add_client(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len,
                    int32_t center_freq, int *client_id);
+/* Dynamic state of one client (what src/xlating.c:29,36 keep between calls). */
+typedef struct {
+  int64_t valid_history; /* add: how many samples before the current stream position this client has really consumed
+                            (older ones read as zero for it); ignored on output */
+  int64_t hist;          /* history_offset: samples of the stream already consumed that precede its next window */
+  float phase_re, phase_im; /* oscillator */
+} xlg_client_state;
+/* Attach a client that CONTINUES: it has already consumed the last `valid_history` samples of this stream
+ * somewhere else (the per-filter ABI) and carries on here with that decimation phase and oscillator.
+ * state == NULL is xlg_add_client (a fresh filter: hist = taps_len-1 zeros, oscillator 1+0i). */
+int xlg_add_client_ex(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len, int32_t center_freq,
+                      const xlg_client_state *state, int *client_id);
 int xlg_remove_client(xlg_group *g, int client_id);
 int xlg_client_count(const xlg_group *g);
 
@@ -105,6 +120,13 @@ int xlg_output(xlg_group *g, int64_t ticket, int client_id, const void **out, si
  * HBM for XLG_OUT_DEVICE groups (a synchronous D2H copy: verification and tools, not
  * the data path).  *out_len = complex samples the client produced. */
 int xlg_read_output(xlg_group *g, int64_t ticket, int client_id, void *dst, size_t cap, size_t *out_len);
+
+/* Same copy for a ticket the caller KNOWS to be complete (it, or another thread, returned from xlg_wait):
+ * makes no CUDA call, so hundreds of consumer threads can call it per block without queueing on the
+ * CUDA context.  Host-output groups only.  With XLG_TRACK_STATE, *state_after (may be NULL) receives the
+ * client's history_offset and oscillator after this ticket.  -ESTALE if the ring entry was recycled. */
+int xlg_copy_output(xlg_group *g, int64_t ticket, int client_id, void *dst, size_t cap, size_t *out_len,
+                    xlg_client_state *state_after);
 
 /* Pinned host memory for input blocks (queue/ingest buffers). */
 void *xlg_alloc_pinned(size_t bytes);
@@ -153,6 +175,12 @@ int xlg_client_info(const xlg_group *g, int client_id, size_t *history, int *ker
  * reference's per-client copies of one SDR block, src/queue.c:114).  -ENOENT before
  * the first filter was created there. */
 int xlg_dropin_stats(int device, uint64_t *batches, uint64_t *calls, uint64_t *shared_inputs);
+
+/* Counters of the drop-in engine's stream overlay on `device` (csrc/stream_overlay.h): stats7[0] process_*
+ * calls served by a band's batch group, [1] blocks published (submitted once for all member filters),
+ * [2] calls that found their block already published, [3] filters that fell out of step and left a group,
+ * [4] filters that joined one, [5] private calls whose block was in the log, [6] filters that are members now. */
+int xlg_dropin_stream_stats(int device, uint64_t *stats7);
 
 #ifdef __cplusplus
 }

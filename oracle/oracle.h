@@ -60,6 +60,12 @@ size_t orc_xlating_history(const orc_xlating *f);
 void orc_xlating_phase(const orc_xlating *f, float *re, float *im);
 size_t orc_xlating_taps(const orc_xlating *f, const float **rev_taps_interleaved);
 
+/* State hand-over, for the model check of the drop-in engine's stream overlay
+ * (tests/stream_overlay_shim.cpp): the cf32 history the next call will prepend
+ * (`hist` complex samples, interleaved; src/xlating.c:76-79) and the oscillator (:36). */
+size_t orc_xlating_get_history(const orc_xlating *f, const float **samples_interleaved);
+int orc_xlating_set_state(orc_xlating *f, const float *history_interleaved, size_t hist, float ph_re, float ph_im);
+
 #ifdef __cplusplus
 }
 #endif

@@ -240,3 +240,17 @@ size_t orc_xlating_taps(const orc_xlating *f, const float **rev) {
   *rev = f->rev_f32;
   return f->ntaps;
 }
+
+size_t orc_xlating_get_history(const orc_xlating *f, const float **samples_interleaved) {
+  *samples_interleaved = f->work_f32; /* the history sits at the front of the work buffer */
+  return f->hist;
+}
+
+int orc_xlating_set_state(orc_xlating *f, const float *history_interleaved, size_t hist, float ph_re, float ph_im) {
+  if (hist > f->ntaps) return -1;
+  memcpy(f->work_f32, history_interleaved, sizeof(float) * 2 * hist);
+  f->hist = hist;
+  f->ph_re = ph_re;
+  f->ph_im = ph_im;
+  return 0;
+}

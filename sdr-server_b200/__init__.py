@@ -36,6 +36,7 @@ XLG_OUT_DEVICE = 0x1
 XLG_NO_RENORM = 0x2
 XLG_FORCE_GENERIC = 0x4
 XLG_SM_PARTITION = 0x10
+XLG_TRACK_STATE = 0x20
 XLG_INPUT_DEVICE = 0x100
 XLG_PATH_Q15 = 0x200
 XLG_INPUT_KEEP = 0x400
@@ -47,9 +48,9 @@ REFERENCE_SYMBOLS = (
     + [f"process_{v}_{f}_{o}" for v in ("native", "optimized") for f in ("cu8", "cs8", "cs16") for o in ("cf32", "cs16")]
 )
 GROUP_SYMBOLS = [
-    "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_remove_client", "xlg_client_count", "xlg_submit",
-    "xlg_wait", "xlg_input_consumed", "xlg_output", "xlg_read_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
-    "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats",
+    "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_add_client_ex", "xlg_remove_client", "xlg_client_count", "xlg_submit",
+    "xlg_wait", "xlg_input_consumed", "xlg_output", "xlg_read_output", "xlg_copy_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
+    "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats", "xlg_dropin_stream_stats",
 ]
 
 
@@ -158,6 +159,19 @@ def dropin_stats(device: int = 0):
     if rc != 0:
         raise RuntimeError(f"xlg_dropin_stats -> {rc}")
     return b.value, c.value, s.value
+
+
+def dropin_stream_stats(device: int = 0) -> dict:
+    """Counters of the drop-in engine's stream overlay (csrc/stream_overlay.h)."""
+    arr = (C.c_uint64 * 7)()
+    fn = lib().xlg_dropin_stream_stats
+    fn.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
+    fn.restype = C.c_int
+    rc = fn(device, arr)
+    if rc != 0:
+        raise RuntimeError(f"xlg_dropin_stream_stats -> {rc}")
+    keys = ("served_by_group", "published", "hits", "desyncs", "joins", "private_matches", "members")
+    return dict(zip(keys, [int(v) for v in arr]))
 
 
 def create_low_pass_filter(gain: float, sampling_freq: int, cutoff_freq: int, transition_width: int) -> np.ndarray:

@@ -1,0 +1,318 @@
+/*
+ * csrc/stream_overlay.h -- "the filters of one SDR stream are one batch", discovered
+ * behind the reference's per-filter ABI.  Host logic only (no CUDA in here: the owner
+ * supplies the group operations, so tests/test_stream_overlay.py can exercise the
+ * state machine on a CPU against the oracle).
+ *
+ * Why.  The reference gives every client a filter and a dsp thread; sdr_callback
+ * memcpy's each SDR block into every client's queue (src/tcp_server.c:262-269 ->
+ * src/queue.c:114) and every dsp thread calls process_* on its private copy
+ * (src/dsp_worker.c:49-72).  The library is therefore handed the SAME block sequence C
+ * times, by C threads, and the fast way to serve that is the batch engine
+ * (include/xlating_group.h): one H2D copy, one fused launch for all clients.  This
+ * class finds that structure at run time, without trusting anything but bytes:
+ *
+ *   * a LOG of the last R blocks of "the stream": pinned copies, in publication order;
+ *     block k was submitted ONCE to a batch group for every member filter;
+ *   * a filter that is a MEMBER expects block pos of the log next.  Its call compares its
+ *     input with that entry (memcmp, always -- the sampled key only short-cuts
+ *     mismatches), waits for the block's ticket and copies ITS row of the result.  The
+ *     first member to arrive with a block the log does not hold yet PUBLISHES it: copies
+ *     it into the log, submits it to the group for everybody, and wakes the others when
+ *     the GPU is done;
+ *   * a member whose input is NOT the expected block (its queue dropped a block,
+ *     src/queue.c:90-94; it lagged more than R blocks; it is fed by another source) is
+ *     DESYNCED: it leaves the group and is served by the per-filter engine from then on,
+ *     starting from its own mirror of the state (the caller keeps that mirror: history
+ *     tail, history_offset, oscillator as of the last block it really consumed) -- every
+ *     group result computed for blocks it did not consume is simply never read;
+ *   * a PRIVATE filter tracks the log too: once the blocks it has consumed are the log's
+ *     newest ones (a run covering its history, or everything since it was created) it
+ *     JOINS the group with its state (xlg_add_client_ex) and is a member from the next
+ *     block on.
+ *
+ * Everything a filter returns is therefore either the private engine's result for the
+ * bytes it was given, or the group's result for a block whose bytes were compared equal
+ * to the ones it was given, computed from a state that consumed exactly the blocks the
+ * filter consumed: results never depend on scheduling, only speed does.
+ *
+ * Publishing rule for private filters: only a filter that is "in step" (it consumed the
+ * log's newest block) may append a block -- or anybody while the stream has no members
+ * yet (bootstrap).  A filter fed by a different source can then never push a foreign
+ * block between the members and their next block.
+ */
+#ifndef XLATING_B200_STREAM_OVERLAY_H_
+#define XLATING_B200_STREAM_OVERLAY_H_
+
+#include <errno.h>
+#include <limits.h>
+#include <linux/futex.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "block_cache.h"  // block_key()
+
+namespace xl {
+
+struct StreamOps {
+  void *ctx;
+  // page-locked memory for the log's block copies
+  void *(*alloc_block)(void *ctx, size_t bytes);
+  void (*free_block)(void *ctx, void *p);
+  // submit one block (already in a log entry's pinned buffer) for ALL members; asynchronous
+  int (*submit)(void *ctx, int fmt, const void *block, size_t elems, int64_t *ticket);
+  // block until the ticket's results are readable
+  int (*wait)(void *ctx, int64_t ticket);
+  // attach `filter` (opaque) which has consumed the last `valid_history` samples of the stream
+  int (*add)(void *ctx, void *filter, int64_t valid_history, int *client);
+  int (*remove)(void *ctx, int client);
+};
+
+class AutoStream {
+ public:
+  struct Member {          // one per filter, owned by the filter; only its own thread touches it
+    bool member = false;
+    int client = -1;       // group client id while a member
+    int64_t pos = -1;      // log index of the block this filter consumes next (-1: not tracking)
+    int64_t run = 0;       // samples of CONSECUTIVE log blocks consumed, ending at pos-1
+  };
+  struct Served {
+    int64_t ticket;
+    int client;
+  };
+  struct Stats {
+    uint64_t published, hits, desyncs, joins, private_matches;
+  };
+
+  AutoStream(const StreamOps &ops, int ring, size_t max_block_bytes)
+      : ops_(ops), ring_(ring < 4 ? 4 : ring), max_bytes_(max_block_bytes), log_((size_t)(ring < 4 ? 4 : ring)) {}
+  ~AutoStream() {
+    for (Entry &e : log_)
+      if (e.host != nullptr) ops_.free_block(ops_.ctx, e.host);
+  }
+  AutoStream(const AutoStream &) = delete;
+  AutoStream &operator=(const AutoStream &) = delete;
+
+  int ring() const { return ring_; }
+  int members() const { return n_members_.load(); }
+
+  // ---- member path.  1: served (the ticket is complete, copy your row); 0: not served,
+  // the filter is now private (it was desynced and has left the group) -- process the
+  // block privately and call private_observe(); never fails otherwise.
+  int member_call(Member &m, const void *input, size_t bytes, int fmt, size_t elems, Served *sv) {
+    if (!m.member) return 0;
+    const int64_t k = m.pos;
+    for (;;) {
+      const int64_t h = head_.load(std::memory_order_acquire);
+      if (k <= h) {
+        Entry &e = log_[(size_t)(k % ring_)];
+        if (!matches(e, k, input, bytes, fmt)) break;  // recycled or different bytes: desync
+        if (!wait_done(e, k)) break;
+        const int64_t ticket = e.ticket;
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (e.seq.load() != k) break;
+        sv->ticket = ticket;
+        sv->client = m.client;
+        m.pos = k + 1;
+        m.run += (int64_t)(elems / 2);
+        hits_.fetch_add(1, std::memory_order_relaxed);
+        return 1;
+      }
+      // k == h + 1: nobody has brought this block yet
+      int64_t ticket = -1;
+      const int rc = publish(k, h, input, bytes, fmt, elems, &ticket);
+      if (rc == 1) continue;  // somebody else published meanwhile: compare with theirs
+      if (rc < 0) break;      // the group refused the block: serve it privately
+      sv->ticket = ticket;
+      sv->client = m.client;
+      m.pos = k + 1;
+      m.run += (int64_t)(elems / 2);
+      return 1;
+    }
+    leave(m);
+    desyncs_.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+
+  // ---- private path bookkeeping: call for every cf32 block a non-member consumes, BEFORE it is
+  // processed (so that members are not kept waiting for a block this caller brings first).  With
+  // retry = true (call again after the private processing if the first call returned false) only
+  // looks the block up.  Returns whether the block is now known to be block m.pos-1 of the log.
+  bool private_observe(Member &m, const void *input, size_t bytes, int fmt, size_t elems, bool retry = false) {
+    if (m.member) return false;
+    const int64_t n = (int64_t)(elems / 2);
+    const uint64_t key = bytes > 0 ? block_key(input, bytes) : 0;
+    for (;;) {
+      const int64_t h = head_.load(std::memory_order_acquire);
+      // the expected next block first, then the newest few
+      if (m.pos >= 0 && m.pos <= h && matches(log_[(size_t)(m.pos % ring_)], m.pos, input, bytes, fmt, &key)) {
+        m.pos += 1;
+        m.run += n;
+        private_matches_.fetch_add(1, std::memory_order_relaxed);
+        return true;
+      }
+      for (int64_t k = h; k >= 0 && k > h - 4; k--) {
+        if (k == m.pos) continue;
+        if (matches(log_[(size_t)(k % ring_)], k, input, bytes, fmt, &key)) {
+          m.pos = k + 1;  // a new run starts with this block
+          m.run = n;
+          private_matches_.fetch_add(1, std::memory_order_relaxed);
+          return true;
+        }
+      }
+      if (retry) break;
+      // not in the log.  May this caller append it?
+      const bool in_step = m.pos == h + 1 && m.run > 0;
+      if (!in_step && n_members_.load() > 0) break;
+      int64_t ticket = -1;
+      const int rc = publish(h + 1, h, input, bytes, fmt, elems, &ticket);
+      if (rc == 1) continue;  // raced with another publisher: look again
+      if (rc < 0) break;
+      m.run = in_step ? m.run + n : n;
+      m.pos = h + 2;
+      return true;
+    }
+    if (retry) {
+      m.pos = -1;
+      m.run = 0;
+    }
+    return false;
+  }
+
+  // ---- after a private block: become a member from the next block on, if this filter's
+  // consumed blocks are exactly the log's newest ones.  needed_history = samples of real history
+  // the filter's next window can reach back (taps_len - 1); total_consumed = all samples it has
+  // consumed since it was created.  The caller's state (history_offset, oscillator) must be that
+  // after its last consumed block; `filter` is handed to StreamOps::add.
+  bool try_join(Member &m, int64_t needed_history, int64_t total_consumed, void *filter) {
+    if (m.member || m.pos < 0 || m.run <= 0) return false;
+    if (m.run < needed_history && m.run != total_consumed) return false;
+    std::lock_guard<std::mutex> lk(mu_);
+    if (m.pos != head_.load() + 1) return false;  // not caught up: the newest block is not its last one
+    int client = -1;
+    if (ops_.add(ops_.ctx, filter, m.run, &client) != 0) return false;
+    m.member = true;
+    m.client = client;
+    n_members_.fetch_add(1);
+    joins_.fetch_add(1, std::memory_order_relaxed);
+    return true;
+  }
+
+  // leave the group (desync, a Q15 call, destroy).  The filter keeps no claim on the log.
+  void leave(Member &m) {
+    if (m.member) {
+      std::lock_guard<std::mutex> lk(mu_);
+      ops_.remove(ops_.ctx, m.client);
+      n_members_.fetch_sub(1);
+    }
+    m.member = false;
+    m.client = -1;
+    m.pos = -1;
+    m.run = 0;
+  }
+
+  Stats stats() const {
+    return Stats{published_.load(), hits_.load(), desyncs_.load(), joins_.load(), private_matches_.load()};
+  }
+
+ private:
+  struct Entry {
+    std::atomic<int64_t> seq{-1};  // log index held, -1 while being (re)written
+    uint64_t key = 0;
+    size_t bytes = 0;
+    int fmt = 0;
+    void *host = nullptr;          // pinned copy of the block
+    int64_t ticket = -1;
+    // futex word: (log index << 2) | state, state 0 = pending, 1 = results readable, 2 = failed.
+    // The index is part of the word because the thread that published block k may be
+    // preempted between the GPU finishing and its store: by then the entry may hold
+    // block k + R, and a plain "done = 1" would release that block's readers early.
+    std::atomic<int> done{-1};
+  };
+
+  static void futex_wait(std::atomic<int> *w, int expected) {
+    syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAIT_PRIVATE, expected, nullptr, nullptr, 0);
+  }
+  static void futex_wake_all(std::atomic<int> *w) {
+    syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+  }
+
+  // entry holds log block k and its bytes equal input's (seqlock: the entry may be recycled
+  // by a publisher while we compare)
+  bool matches(Entry &e, int64_t k, const void *input, size_t bytes, int fmt, const uint64_t *key = nullptr) {
+    if (e.seq.load(std::memory_order_acquire) != k) return false;
+    if (e.bytes != bytes || e.fmt != fmt) return false;
+    if (key != nullptr && e.key != *key) return false;
+    if (bytes > 0 && memcmp(e.host, input, bytes) != 0) return false;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return e.seq.load() == k;
+  }
+
+  static int done_tag(int64_t k) { return (int)((uint32_t)(k & 0x1fffffff) << 2); }
+
+  bool wait_done(Entry &e, int64_t k) {
+    const int tag = done_tag(k);
+    for (;;) {
+      const int d = e.done.load(std::memory_order_acquire);
+      if (e.seq.load() != k) return false;  // recycled: this filter lagged a whole ring
+      if (d == (tag | 1)) return true;
+      if (d == (tag | 2)) return false;
+      if (d == tag) futex_wait(&e.done, tag);
+    }
+  }
+
+  // Append block k = h+1.  0: published by this caller and complete; 1: head moved
+  // (someone else published); <0: error, nothing published.
+  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, int64_t *ticket) {
+    Entry *e = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (head_.load() != h) return 1;
+      if (bytes > max_bytes_) return -EINVAL;
+      e = &log_[(size_t)(k % ring_)];
+      e->seq.store(-1);  // readers of the old block back off
+      if (e->host == nullptr) {
+        e->host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
+        if (e->host == nullptr) return -ENOMEM;
+      }
+      memcpy(e->host, input, bytes);
+      e->key = bytes > 0 ? block_key(input, bytes) : 0;
+      e->bytes = bytes;
+      e->fmt = fmt;
+      e->done.store(done_tag(k));
+      int64_t t = -1;
+      const int rc = ops_.submit(ops_.ctx, fmt, e->host, elems, &t);
+      if (rc != 0) return rc < 0 ? rc : -EIO;  // entry stays invalid (seq = -1), head unchanged
+      e->ticket = t;
+      e->seq.store(k, std::memory_order_release);
+      head_.store(k, std::memory_order_release);
+      published_.fetch_add(1, std::memory_order_relaxed);
+      *ticket = t;
+    }
+    // outside the lock: the next block can be published while this one computes
+    const int rc = ops_.wait(ops_.ctx, *ticket);
+    int pending = done_tag(k);
+    e->done.compare_exchange_strong(pending, done_tag(k) | (rc == 0 ? 1 : 2));  // fails if the entry was recycled
+    futex_wake_all(&e->done);
+    return rc == 0 ? 0 : -EIO;
+  }
+
+  const StreamOps ops_;
+  const int ring_;
+  const size_t max_bytes_;
+  std::vector<Entry> log_;
+  std::mutex mu_;  // serialises publishers and membership changes (= all group mutations)
+  std::atomic<int64_t> head_{-1};
+  std::atomic<int> n_members_{0};
+  std::atomic<uint64_t> published_{0}, hits_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
+};
+
+}  // namespace xl
+#endif

@@ -40,6 +40,19 @@
  * Filters keep private state (ring, oscillator, history) on the device; results
  * are independent of how calls happen to be batched.
  *
+ * One stream, one batch (stream_overlay.h).  When several filters of one band
+ * (same device, sampling rate and block size) are alive, their calls are first matched
+ * against a log of "the stream": the dsp threads of the reference all consume the same
+ * block sequence, so the first thread that brings a block submits it ONCE to a batch group
+ * (include/xlating_group.h: one H2D copy, one fused tiled launch for all member filters)
+ * and every other thread only compares its bytes with the log entry (memcmp, always),
+ * sleeps until the GPU is done and copies its own row of the result.  A filter whose
+ * input is not the stream's next block (its queue dropped one, it lags a whole ring, it
+ * is fed by another source) leaves the group and is served by the combined per-filter
+ * engine below from its own mirror of the state; it rejoins when it is in step again.
+ * XLATING_B200_STREAM=0 turns this off, XLATING_B200_STREAM_RING=<blocks> sizes the log
+ * and the group's result ring (default 64 = the reference's queue_size, src/config.c:183).
+ *
  * XLATING_B200_DROPIN=group selects the older model instead (each filter a private
  * one-client batch group with its own streams), kept for A/B measurements.
  */
@@ -59,6 +72,7 @@
 #include "block_cache.h"
 #include "call_combiner.h"
 #include "dropin_kernels.cuh"
+#include "stream_overlay.h"
 #include "taps_host.h"
 #include "xl_log.h"
 #include "xlating.h"
@@ -98,6 +112,19 @@ struct Lane {
   int2 *d_batch = nullptr;           // (filter, q15) per request, written by the front kernel
 };
 
+struct Engine;
+
+// One SDR band as the overlay sees it: filters created with the same sampling rate and
+// block size on one device.  The batch group and the stream log exist only while at least
+// two such filters are alive (a lone filter keeps its 46 us private path).
+struct StreamHost {
+  Engine *e = nullptr;
+  uint32_t fs = 0, max_in = 0;
+  int refs = 0;                          // filters with this key (guarded by Engine::mu)
+  xlg_group *g = nullptr;
+  std::atomic<AutoStream *> as{nullptr};
+};
+
 struct Engine {
   int device = 0;
   CallCombiner *combiner = nullptr;
@@ -114,7 +141,25 @@ struct Engine {
   bool share_inputs = true;                    // XLATING_B200_SHARE=0 turns the cache off
   bool osc_lanes = false;                      // XLATING_B200_OSC=lanes: oscillator chains share one warp (A/B)
   bool osc_host = kOscHostDefault;             // XLATING_B200_OSC=host|device: who walks the cf32 oscillator
+  // Memory of destroyed filters, kept for the next create: destroy_xlating is then a few
+  // microseconds like the reference's free() (src/xlating.c:584-616) instead of two
+  // synchronising CUDA frees.  The reference's tcp threads tear a client down while
+  // holding the server mutex (src/tcp_server.c:231-254) and its server test relies on
+  // that being quick (test/test_tcp_server.c:43-63: a late close() of an already closed
+  // descriptor must not land after the descriptor number has been reused).
+  struct Pooled {
+    void *d_mem, *h_mem;
+    size_t d_bytes, h_bytes;
+  };
+  std::vector<Pooled> pool;  // guarded by mu
+  size_t pool_bytes = 0;
+  // stream overlay (stream_overlay.h)
+  bool overlay = true;       // XLATING_B200_STREAM=0 turns it off
+  int stream_ring = 64;      // XLATING_B200_STREAM_RING
+  std::vector<StreamHost *> streams;  // guarded by mu
+  std::atomic<uint64_t> stream_served{0};
 };
+constexpr size_t kPoolMaxBytes = (size_t)2 << 30;  // device + pinned bytes kept for reuse
 
 constexpr size_t kShareMinBytes = 4096;  // smaller inputs are not worth hashing
 static_assert(BlockCache::kSlots <= 32, "run_batch keeps the referenced entries in a 32-bit mask");
@@ -173,6 +218,7 @@ struct xlating_t {
   long long S = 0, qS = 0;  // samples consumed so far by the cf32 / Q15 path
   void *d_mem = nullptr;    // ring | qring | taps | qtaps | phases | qphases
   void *h_mem = nullptr;    // pinned: staged input | cf32 output | Q15 output
+  size_t d_bytes = 0, h_bytes = 0;
   void *h_in = nullptr;
   const void *d_in = nullptr;  // device address of h_in (zero-copy)
   float2 *h_out = nullptr;
@@ -180,6 +226,18 @@ struct xlating_t {
   float *h_phases = nullptr;  // pinned oscillator table (host-walked chain), read by the FIR kernel
   float ph_re = 1.0f, ph_im = 0.0f, inc_re = 0.0f, inc_im = 0.0f;  // host oscillator (src/xlating.c:543-544)
   bool osc_deferred = false;  // this call's chain is still to be walked (by the batch leader)
+  // --- stream overlay: membership in the band's batch group, and the mirror of the state
+  // after the last block this filter really consumed (hist, ph_re/ph_im above, tail below),
+  // from which either engine can carry on
+  StreamHost *sh = nullptr;
+  AutoStream::Member as_m;
+  int32_t center_freq = 0;
+  uint32_t fs = 0;
+  bool as_disabled = false;   // a Q15 call was made: the two paths share history_offset, stay private
+  bool dev_stale = false;     // the private device state is behind the mirror (group served the last blocks)
+  std::vector<float2> tail;   // the last T-1 samples consumed (cf32), oldest first, zeros before the first
+  float2 *d_ring = nullptr;   // the filter's private cf32 ring (inside d_mem) and its size
+  size_t ring_cap = 0;
   // the call in flight
   DropinReq req;
   int req_out = 0;
@@ -190,6 +248,95 @@ struct xlating_t {
 namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- stream overlay: group operations (StreamOps) ----
+void *stream_alloc(void *ctx, size_t bytes) {
+  StreamHost *sh = (StreamHost *)ctx;
+  void *p = nullptr;
+  if (cudaSetDevice(sh->e->device) != cudaSuccess || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void stream_free(void *ctx, void *p) {
+  cudaSetDevice(((StreamHost *)ctx)->e->device);
+  cudaFreeHost(p);
+}
+int stream_submit(void *ctx, int fmt, const void *block, size_t elems, int64_t *ticket) {
+  StreamHost *sh = (StreamHost *)ctx;
+  // the log entry is page-locked and stays untouched for a whole ring of blocks
+  const int64_t t = xlg_submit(sh->g, fmt, block, elems, XLG_INPUT_KEEP);
+  if (t < 0) return (int)t;
+  *ticket = t;
+  return 0;
+}
+int stream_wait(void *ctx, int64_t ticket) { return xlg_wait(((StreamHost *)ctx)->g, ticket); }
+int stream_add(void *ctx, void *filter, int64_t valid_history, int *client) {
+  StreamHost *sh = (StreamHost *)ctx;
+  const xlating *f = (const xlating *)filter;
+  xlg_client_state st;
+  st.valid_history = valid_history;
+  st.hist = f->hist;
+  st.phase_re = f->ph_re;
+  st.phase_im = f->ph_im;
+  return xlg_add_client_ex(sh->g, f->D, f->adopted_taps, (size_t)f->T, f->center_freq, &st, client);
+}
+int stream_remove(void *ctx, int client) { return xlg_remove_client(((StreamHost *)ctx)->g, client); }
+
+// host twins of the device conversions (xlating_common.cuh: all exact)
+inline float2 host_sample(int fmt, const void *input, size_t i) {
+  if (fmt == XLG_FMT_CU8) {
+    const uint8_t *u = (const uint8_t *)input + 2 * i;
+    return make_float2(((float)u[0] - 127.5f) * 0.0078125f, ((float)u[1] - 127.5f) * 0.0078125f);
+  }
+  if (fmt == XLG_FMT_CS8) {
+    const int8_t *u = (const int8_t *)input + 2 * i;
+    return make_float2((float)u[0] * 0.0078125f, (float)u[1] * 0.0078125f);
+  }
+  const int16_t *u = (const int16_t *)input + 2 * i;
+  return make_float2((float)u[0] * (1.0f / 32768.0f), (float)u[1] * (1.0f / 32768.0f));
+}
+
+// the last T-1 samples of (tail ++ block)
+void tail_push(xlating *f, int fmt, const void *input, size_t n) {
+  const size_t keep = f->tail.size();
+  if (keep == 0) return;
+  if (n >= keep) {
+    for (size_t i = 0; i < keep; i++) f->tail[i] = host_sample(fmt, input, n - keep + i);
+  } else {
+    memmove(f->tail.data(), f->tail.data() + n, sizeof(float2) * (keep - n));
+    for (size_t i = 0; i < n; i++) f->tail[keep - n + i] = host_sample(fmt, input, i);
+  }
+}
+
+// The group served this filter's last blocks: bring the PRIVATE device state up to the
+// mirror before the per-filter engine runs again (history into the private ring at the
+// positions the next call's window reads, history_offset, oscillator).
+int sync_device_state(xlating *f) {
+  cudaError_t err = cudaSetDevice(f->e->device);
+  const size_t keep = f->tail.size();
+  const unsigned mask = (unsigned)(f->ring_cap - 1);
+  for (size_t done = 0; done < keep && err == cudaSuccess;) {
+    const unsigned idx = (unsigned)((unsigned long long)(f->S - (long long)keep + (long long)done)) & mask;
+    const size_t run = std::min(keep - done, (size_t)(mask + 1u - idx));
+    err = cudaMemcpy(f->d_ring + idx, f->tail.data() + done, run * sizeof(float2), cudaMemcpyHostToDevice);
+    done += run;
+  }
+  FilterDev *d = f->e->d_filters + f->slot;
+  const long long hist = f->hist;
+  const float2 ph = make_float2(f->ph_re, f->ph_im);
+  if (err == cudaSuccess)
+    err = cudaMemcpy((char *)d + offsetof(FilterDev, hist), &hist, sizeof(hist), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess)
+    err = cudaMemcpy((char *)d + offsetof(FilterDev, phase), &ph, sizeof(ph), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    XL_LOG("could not restore a filter's private state: %s", cudaGetErrorString(err));
+    return -EIO;
+  }
+  f->dev_stale = false;
+  return 0;
+}
 
 // Launch one batch on lane `lane` and wait for it (CallCombiner::RunBatch; called by the
 // batch's leader thread).
@@ -273,6 +420,10 @@ int engine_get(int device, Engine **out) {
     if (e->n_lanes > kMaxLanes) e->n_lanes = kMaxLanes;
     env = getenv("XLATING_B200_SHARE");
     e->share_inputs = !(env != nullptr && strcmp(env, "0") == 0);
+    env = getenv("XLATING_B200_STREAM");
+    e->overlay = !(env != nullptr && strcmp(env, "0") == 0);
+    env = getenv("XLATING_B200_STREAM_RING");
+    if (env != nullptr) e->stream_ring = std::min(std::max(atoi(env), 4), 1024);
     env = getenv("XLATING_B200_OSC");
     e->osc_lanes = env != nullptr && strcmp(env, "lanes") == 0;
     if (env != nullptr && strcmp(env, "host") == 0) e->osc_host = true;
@@ -306,14 +457,96 @@ fail:
   return rc;
 }
 
+void stream_detach(xlating *f) {
+  StreamHost *sh = f->sh;
+  if (sh == nullptr) return;
+  AutoStream *as = sh->as.load();
+  if (as != nullptr) as->leave(f->as_m);
+  f->sh = nullptr;
+  Engine *e = sh->e;
+  AutoStream *dead_as = nullptr;
+  xlg_group *dead_g = nullptr;
+  bool last = false;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (--sh->refs == 0) {
+      last = true;
+      // nobody can reach the stream any more: filters find it only through their own sh
+      dead_as = sh->as.exchange(nullptr);
+      dead_g = sh->g;
+      for (size_t i = 0; i < e->streams.size(); i++)
+        if (e->streams[i] == sh) {
+          e->streams.erase(e->streams.begin() + (long)i);
+          break;
+        }
+    }
+  }
+  if (last) {
+    delete dead_as;  // frees the log's pinned blocks (before the group: its callbacks use sh)
+    if (dead_g != nullptr) xlg_destroy(dead_g);
+    delete sh;
+  }
+}
+
+// The band's stream: found or created when a filter is built; the batch group and the log
+// come to life with the second filter of the band.
+void stream_attach(xlating *f, uint32_t fs, uint32_t max_in) {
+  Engine *e = f->e;
+  if (!e->overlay || !e->osc_host) return;  // the mirror needs the host-walked oscillator
+  StreamHost *sh = nullptr;
+  bool start = false;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    for (StreamHost *c : e->streams)
+      if (c->fs == fs && c->max_in == max_in) sh = c;
+    if (sh == nullptr) {
+      sh = new (std::nothrow) StreamHost();
+      if (sh == nullptr) return;
+      sh->e = e;
+      sh->fs = fs;
+      sh->max_in = max_in;
+      e->streams.push_back(sh);
+    }
+    sh->refs++;
+    start = sh->refs >= 2 && sh->as.load() == nullptr && sh->g == nullptr;
+    if (start) {
+      // still under e->mu: one creator.  (xlg_create_ex is slow -- pinned staging, streams --
+      // but it happens once per band.)
+      if (xlg_create_ex(e->device, fs, max_in, XLG_TRACK_STATE, (uint32_t)e->stream_ring, &sh->g) == 0) {
+        const StreamOps ops = {sh, stream_alloc, stream_free, stream_submit, stream_wait, stream_add, stream_remove};
+        AutoStream *as = new (std::nothrow) AutoStream(ops, e->stream_ring, (size_t)max_in * sizeof(int16_t));
+        if (as != nullptr) {
+          sh->as.store(as);
+        } else {
+          xlg_destroy(sh->g);
+          sh->g = nullptr;
+        }
+      } else {
+        sh->g = nullptr;
+      }
+    }
+  }
+  f->sh = sh;
+}
+
 void filter_release(xlating *f) {
+  stream_detach(f);
   if (f->e != nullptr) {
-    cudaSetDevice(f->e->device);
-    if (f->d_mem != nullptr) cudaFree(f->d_mem);
-    if (f->h_mem != nullptr) cudaFreeHost(f->h_mem);
-    if (f->slot >= 0) {
+    bool pooled = false;
+    {
       std::lock_guard<std::mutex> lk(f->e->mu);
-      f->e->free_slots.push_back(f->slot);
+      if (f->slot >= 0) f->e->free_slots.push_back(f->slot);
+      if (f->d_mem != nullptr && f->h_mem != nullptr &&
+          f->e->pool_bytes + f->d_bytes + f->h_bytes <= kPoolMaxBytes) {
+        f->e->pool.push_back({f->d_mem, f->h_mem, f->d_bytes, f->h_bytes});
+        f->e->pool_bytes += f->d_bytes + f->h_bytes;
+        pooled = true;
+      }
+    }
+    if (!pooled) {
+      cudaSetDevice(f->e->device);
+      if (f->d_mem != nullptr) cudaFree(f->d_mem);
+      if (f->h_mem != nullptr) cudaFreeHost(f->h_mem);
     }
     if (f->counted) f->e->live_filters--;
   }
@@ -358,12 +591,35 @@ int filter_build(xlating *f, int device, uint32_t decimation, const float *taps,
   const size_t h_ph_bytes = align_up(((size_t)f->out_cap / 2 + 2) * sizeof(float2), 256);
   char *dm = nullptr, *hm = nullptr, *hm_dev = nullptr;
   CU_TRY(cudaSetDevice(device));
-  CU_TRY(cudaMalloc(&f->d_mem, d_bytes));
+  {
+    // memory of a destroyed filter of the same shape, if any
+    std::lock_guard<std::mutex> lk(f->e->mu);
+    const size_t h_need = h_in_bytes + h_out_bytes + h_qout_bytes + h_ph_bytes;
+    for (size_t i = 0; i < f->e->pool.size(); i++) {
+      const Engine::Pooled &p = f->e->pool[i];
+      if (p.d_bytes >= d_bytes && p.h_bytes >= h_need && p.d_bytes <= 2 * d_bytes && p.h_bytes <= 2 * h_need) {
+        f->d_mem = p.d_mem;
+        f->h_mem = p.h_mem;
+        f->d_bytes = p.d_bytes;
+        f->h_bytes = p.h_bytes;
+        f->e->pool_bytes -= p.d_bytes + p.h_bytes;
+        f->e->pool.erase(f->e->pool.begin() + (long)i);
+        break;
+      }
+    }
+  }
+  if (f->d_mem == nullptr) {
+    CU_TRY(cudaMalloc(&f->d_mem, d_bytes));
+    f->d_bytes = d_bytes;
+  }
   dm = (char *)f->d_mem;
   CU_TRY(cudaMemset(dm, 0, o_taps));  // both rings start as the reference's zeroed working buffers (:556-565)
   CU_TRY(cudaMemcpy(dm + o_taps, k.rev_cf32, taps_len * sizeof(float2), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(dm + o_qtaps, k.rev_q15, taps_len * sizeof(short2), cudaMemcpyHostToDevice));
-  CU_TRY(cudaHostAlloc(&f->h_mem, h_in_bytes + h_out_bytes + h_qout_bytes + h_ph_bytes, cudaHostAllocMapped));
+  if (f->h_mem == nullptr) {
+    f->h_bytes = h_in_bytes + h_out_bytes + h_qout_bytes + h_ph_bytes;
+    CU_TRY(cudaHostAlloc(&f->h_mem, f->h_bytes, cudaHostAllocMapped));
+  }
   hm = (char *)f->h_mem;
   CU_TRY(cudaHostGetDevicePointer((void **)&hm_dev, f->h_mem, 0));
   f->h_in = hm;
@@ -373,6 +629,11 @@ int filter_build(xlating *f, int device, uint32_t decimation, const float *taps,
   f->h_phases = (float *)(hm + h_in_bytes + h_out_bytes + h_qout_bytes);
   f->inc_re = k.incr_re;
   f->inc_im = k.incr_im;
+  f->center_freq = center_freq;
+  f->fs = sampling_freq;
+  f->tail.assign(taps_len - 1, make_float2(0.f, 0.f));  // src/xlating.c:552-565: zero history
+  f->d_ring = (float2 *)(dm + o_ring);
+  f->ring_cap = cap;
   d.ring = (float2 *)(dm + o_ring);
   d.qring = (short2 *)(dm + o_qring);
   d.taps = (const float2 *)(dm + o_taps);
@@ -405,6 +666,7 @@ int filter_build(xlating *f, int device, uint32_t decimation, const float *taps,
   f->e->live_filters++;
   f->counted = true;
   xl_client_consts_free(&k);
+  stream_attach(f, sampling_freq, max_in);
   return 0;
 fail:
   xl_client_consts_free(&k);
@@ -456,6 +718,44 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
   if (n == 0) return;
   const size_t bytes = (size_t)n * 2 * (fmt == XLG_FMT_CS16 ? sizeof(int16_t) : 1);
   Engine *e = f->e;
+  // ---- one stream, one batch: is this the band's next block? (stream_overlay.h) ----
+  AutoStream *as = (f->sh != nullptr && !f->as_disabled) ? f->sh->as.load(std::memory_order_acquire) : nullptr;
+  bool observed = false;
+  if (as != nullptr && q15) {
+    as->leave(f->as_m);  // the Q15 path shares history_offset with this one (src/xlating.c:29): stay private
+    f->as_disabled = true;
+    as = nullptr;
+  }
+  if (as != nullptr) {
+    const size_t elems = (size_t)n * 2;
+    AutoStream::Served sv;
+    if (f->as_m.member && as->member_call(f->as_m, input, bytes, fmt, elems, &sv) == 1) {
+      // the group computed this block for every member; take this filter's row and state
+      const long long first = f->S - f->hist;
+      const long long last_ok = f->S + n - f->T;
+      size_t want = 0, got = 0;
+      if (last_ok >= first) want = (size_t)((last_ok - first) / (long long)f->D) + 1;
+      xlg_client_state st;
+      const int rc = xlg_copy_output(f->sh->g, sv.ticket, sv.client, f->h_out, (size_t)f->out_cap, &got, &st);
+      if (rc == 0 && got == want) {
+        f->hist = st.hist;
+        f->ph_re = st.phase_re;
+        f->ph_im = st.phase_im;
+        tail_push(f, fmt, input, (size_t)n);
+        f->S += n;
+        f->dev_stale = true;
+        e->stream_served.fetch_add(1, std::memory_order_relaxed);
+        *output_len = got;
+        return;
+      }
+      // the result ring was recycled under this (slow) caller, or the group disagrees about the
+      // output count: the mirror is untouched, serve the block privately
+      if (rc == 0) XL_LOG("stream group produced %zu outputs where %zu were expected; filter leaves the group", got, want);
+      as->leave(f->as_m);
+    }
+    observed = as->private_observe(f->as_m, input, bytes, fmt, elems);
+  }
+  if (f->dev_stale && sync_device_state(f) != 0) return;
   // other filters exist: they are probably being handed the same bytes (src/queue.c:114)
   int slot = BlockCache::kPrivate;
   if (e->share_inputs && bytes >= kShareMinBytes && e->live_filters.load() >= 2) slot = e->cache->acquire(input, bytes);
@@ -497,6 +797,13 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
     f->qS += n;
   else
     f->S += n;
+  if (!q15) {
+    tail_push(f, fmt, input, (size_t)n);
+    if (as != nullptr && rc == 0) {
+      if (!observed) as->private_observe(f->as_m, input, bytes, fmt, (size_t)n * 2, /*retry=*/true);
+      as->try_join(f->as_m, (int64_t)f->T - 1, (int64_t)f->S, f);
+    }
+  }
   if (rc != 0) {
     XL_LOG("block dropped (%d)", rc);
     return;
@@ -563,6 +870,28 @@ int xlg_dropin_stats(int device, uint64_t *batches, uint64_t *calls, uint64_t *s
   uint64_t hits = 0, publishes = 0;
   it->second->cache->stats(&hits, &publishes);
   if (shared_inputs != NULL) *shared_inputs = hits;
+  return 0;
+}
+
+int xlg_dropin_stream_stats(int device, uint64_t *stats7) {
+  std::lock_guard<std::mutex> lk(g_engines_mu);
+  auto it = g_engines.find(device);
+  if (it == g_engines.end() || stats7 == NULL) return -ENOENT;
+  Engine *e = it->second;
+  memset(stats7, 0, 7 * sizeof(uint64_t));
+  stats7[0] = e->stream_served.load();
+  std::lock_guard<std::mutex> lk2(e->mu);
+  for (StreamHost *sh : e->streams) {
+    AutoStream *as = sh->as.load();
+    if (as == nullptr) continue;
+    const AutoStream::Stats st = as->stats();
+    stats7[1] += st.published;
+    stats7[2] += st.hits;
+    stats7[3] += st.desyncs;
+    stats7[4] += st.joins;
+    stats7[5] += st.private_matches;
+    stats7[6] += (uint64_t)as->members();
+  }
   return 0;
 }
 

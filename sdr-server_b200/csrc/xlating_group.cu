@@ -72,6 +72,7 @@ struct HostClient {
   long long hist = 0;            // mirror of ClientDev::hist
   long long zero_before = 0, qzero_before = 0;
   bool is_new = true;            // dynamic state not yet on the device
+  float init_ph_re = 1.0f, init_ph_im = 0.0f;  // oscillator at attach (src/xlating.c:543, or xlg_add_client_ex)
   int kind = 0;
   int out_off = 0, out_cap = 0;
   int taps_off = 0;
@@ -88,6 +89,7 @@ struct Slot {
   float2 *d_partial = nullptr;  // split-K partial sums of the long-filter classes
   short2 *d_qphases = nullptr;
   BlkInfo *d_blk = nullptr;
+  float2 *d_endph = nullptr;  // XLG_TRACK_STATE: every client's oscillator after this block (same capacity as d_blk)
   size_t blk_cap = 0;
   cudaEvent_t ev_h2d = nullptr, ev_conv = nullptr, ev_phase = nullptr, ev_fir = nullptr, ev_done = nullptr;
   cudaEvent_t pf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -145,6 +147,9 @@ struct HostOut {
   short2 *h_qout = nullptr;
   std::vector<int> n_out;    // per client id
   std::vector<int> out_off;  // per client id
+  std::vector<long long> hist_after;  // XLG_TRACK_STATE: per client id, history_offset after this ticket
+  float2 *h_endph = nullptr;          // XLG_TRACK_STATE: pinned, oscillator after this ticket, per client id
+  size_t endph_cap = 0;
 };
 
 struct TileClassHost {
@@ -234,6 +239,8 @@ static void slot_free(Slot &s) {
   if (s.d_partial) cudaFree(s.d_partial);
   if (s.d_qphases) cudaFree(s.d_qphases);
   if (s.d_blk) cudaFree(s.d_blk);
+  if (s.d_endph) cudaFree(s.d_endph);
+  s.d_endph = nullptr;
   s.d_raw = s.h_raw = nullptr;
   s.d_out = nullptr;
   s.d_qout = nullptr;
@@ -680,7 +687,7 @@ static int rebuild_layout(xlg_group *g) {
       d.hist = h.hist;
       d.zero_before = h.zero_before;
       d.qzero_before = h.qzero_before;
-      d.phase = make_float2(1.0f, 0.0f);  // src/xlating.c:543
+      d.phase = make_float2(h.init_ph_re, h.init_ph_im);  // (1, 0): src/xlating.c:543
       d.incr = make_float2(h.incr_re, h.incr_im);
       d.qph_re = INT16_MAX;  // src/xlating.c:546-547
       d.qph_im = 0;
@@ -715,6 +722,20 @@ static int rebuild_layout(xlg_group *g) {
       s.d_blk = nullptr;
       s.blk_cap = std::max<size_t>((size_t)nc * 2, 64);
       CU_OK(cudaMalloc(&s.d_blk, s.blk_cap * sizeof(BlkInfo)));
+      if (s.d_endph) cudaFree(s.d_endph);
+      s.d_endph = nullptr;
+      if (g->flags & XLG_TRACK_STATE) CU_OK(cudaMalloc(&s.d_endph, s.blk_cap * sizeof(float2)));
+    }
+  }
+  if (g->flags & XLG_TRACK_STATE) {
+    const size_t want = std::max<size_t>((size_t)nc * 2, 64);
+    for (HostOut &h : g->ring_out) {
+      if (h.endph_cap >= (size_t)std::max(nc, 1)) continue;
+      std::lock_guard<std::mutex> lk(g->mu);
+      if (h.h_endph) g->retired_host.push_back(h.h_endph);  // a reader may still hold the old array
+      h.h_endph = nullptr;
+      CU_OK(cudaHostAlloc(&h.h_endph, want * sizeof(float2), cudaHostAllocDefault));
+      h.endph_cap = want;
     }
   }
   g->dirty = false;
@@ -911,6 +932,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
   for (HostOut &h : g->ring_out) {
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_qout) cudaFreeHost(h.h_qout);
+    if (h.h_endph) cudaFreeHost(h.h_endph);
   }
   for (void *p : g->retired_host) cudaFreeHost(p);
   if (g->ev_t0) cudaEventDestroy(g->ev_t0);
@@ -942,7 +964,13 @@ extern "C" void xlg_destroy(xlg_group *g) {
 
 extern "C" int xlg_add_client(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len,
                               int32_t center_freq, int *client_id) {
+  return xlg_add_client_ex(g, decimation, taps, taps_len, center_freq, nullptr, client_id);
+}
+
+extern "C" int xlg_add_client_ex(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len,
+                                 int32_t center_freq, const xlg_client_state *state, int *client_id) {
   if (g == nullptr || client_id == nullptr) return -EINVAL;
+  if (state != nullptr && (state->hist < 0 || state->valid_history < 0 || (size_t)state->hist > taps_len)) return -EINVAL;
   if (taps_len == 0 || taps == nullptr) return -1;  // src/xlating.c:496
   if (decimation == 0) return -EINVAL;
   xl_client_consts k;
@@ -972,6 +1000,15 @@ extern "C" int xlg_add_client(xlg_group *g, uint32_t decimation, const float *ta
   h.hist = (long long)taps_len - 1;  // src/xlating.c:552
   h.zero_before = g->S;
   h.qzero_before = g->qS;
+  if (state != nullptr) {
+    // a filter that already consumed the last `valid_history` samples of this stream elsewhere
+    // (the per-filter drop-in engine) continues here: same decimation phase, same oscillator;
+    // samples further back read as zero, as they did for it
+    h.hist = state->hist;
+    h.zero_before = g->S - state->valid_history;
+    h.init_ph_re = state->phase_re;
+    h.init_ph_im = state->phase_im;
+  }
   h.is_new = true;
   xl_client_consts_free(&k);
   g->dirty = true;
@@ -1070,6 +1107,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     ho.ticket.store(-1);  // the entry is being recycled
     ho.n_out.assign(g->clients.size(), 0);
     ho.out_off.assign(g->clients.size(), 0);
+    if (g->flags & XLG_TRACK_STATE) ho.hist_after.assign(g->clients.size(), 0);
     ho.q15 = q15;
   }
   s.q15 = q15;
@@ -1087,6 +1125,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     ho.n_out[i] = n_out;
     ho.out_off[i] = h.out_off;
     h.hist = (S + n) - (first + (long long)n_out * (long long)h.D);
+    if (g->flags & XLG_TRACK_STATE) ho.hist_after[i] = h.hist;
     s.out_samples += (uint64_t)n_out;
     s.algo_macs += (uint64_t)n_out * h.T;
     if (q15 || h.kind == 0) max_generic_out = std::max(max_generic_out, n_out);
@@ -1155,8 +1194,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       phase_q15_kernel<<<(nc + P_QTHREADS - 1) / P_QTHREADS, P_QTHREADS, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk,
                                                                                       s.d_qphases, S, n);
     else
-      phase_cf32_kernel<<<g->n_order / 32, P_THREADS, 0, g->s_ph>>>(g->d_clients, g->d_order, s.d_blk, s.d_phases, S,
-                                                                   n);
+      phase_cf32_kernel<<<g->n_order / 32, P_THREADS, 0, g->s_ph>>>(g->d_clients, g->d_order, s.d_blk, s.d_phases,
+                                                                   s.d_endph, S, n);
     if (g->profiling) CU_OK(cudaEventRecord(s.pf[3], g->s_ph));
     CU_OK(cudaEventRecord(s.ev_phase, g->s_ph));
     CU_OK(cudaStreamWaitEvent(cs, s.ev_phase, 0));
@@ -1310,6 +1349,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       else
         CU_OK(cudaMemcpyAsync(ho.h_out, s.d_out, used * sizeof(float2), cudaMemcpyDeviceToHost, g->s_out));
     }
+    if ((g->flags & XLG_TRACK_STATE) && !q15 && s.d_endph != nullptr && ho.h_endph != nullptr)
+      CU_OK(cudaMemcpyAsync(ho.h_endph, s.d_endph, (size_t)nc * sizeof(float2), cudaMemcpyDeviceToHost, g->s_out));
     CU_OK(cudaEventRecord(s.ev_done, g->s_out));
   } else {
     CU_OK(cudaStreamWaitEvent(g->s_out, s.ev_fir, 0));
@@ -1390,6 +1431,45 @@ extern "C" int xlg_read_output(xlg_group *g, int64_t ticket, int client_id, void
     if (ho.ticket.load() != ticket) return -ESTALE;
   }
   return 0;
+}
+
+extern "C" int xlg_copy_output(xlg_group *g, int64_t ticket, int client_id, void *dst, size_t cap, size_t *out_len,
+                               xlg_client_state *state_after) {
+  // No CUDA call in here: the caller knows the ticket is complete (it, or the thread that
+  // published the block, returned from xlg_wait); hundreds of consumer threads call this
+  // per block and must not queue up on the CUDA context lock.
+  if (g == nullptr || dst == nullptr || (g->flags & XLG_OUT_DEVICE)) return -EINVAL;
+  if (ticket < 0 || ticket >= g->next_ticket.load()) return -EINVAL;
+  HostOut &ho = g->ring_out[ticket % (int64_t)g->ring_out.size()];
+  const void *src = nullptr;
+  size_t n = 0;
+  long long hist_after = 0;
+  const float2 *endph = nullptr;
+  bool q15 = false;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (ho.ticket.load() != ticket) return -ESTALE;
+    if (client_id < 0 || client_id >= (int)ho.n_out.size()) return -EINVAL;
+    n = (size_t)ho.n_out[client_id];
+    q15 = ho.q15;
+    src = q15 ? (const void *)(ho.h_qout + ho.out_off[client_id]) : (const void *)(ho.h_out + ho.out_off[client_id]);
+    if (state_after != nullptr) {
+      if (!(g->flags & XLG_TRACK_STATE) || q15 || ho.h_endph == nullptr || client_id >= (int)ho.hist_after.size())
+        return -EINVAL;
+      hist_after = ho.hist_after[client_id];
+      endph = ho.h_endph + client_id;
+    }
+  }
+  if (out_len) *out_len = n;
+  memcpy(dst, src, std::min(n, cap) * (q15 ? sizeof(short2) : sizeof(float2)));
+  if (state_after != nullptr) {
+    state_after->hist = hist_after;
+    state_after->valid_history = 0;
+    state_after->phase_re = endph->x;
+    state_after->phase_im = endph->y;
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return ho.ticket.load() == ticket ? 0 : -ESTALE;
 }
 
 extern "C" int xlg_input_consumed(xlg_group *g, int64_t ticket) {

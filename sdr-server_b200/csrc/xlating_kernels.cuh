@@ -123,7 +123,7 @@ constexpr int P_QTHREADS = 64;  // Q15 variant (one thread per client)
 // because a lone warp can only keep ~32 stores in flight.)
 __global__ void __launch_bounds__(P_THREADS)
 phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, BlkInfo *__restrict__ blk,
-                  float2 *__restrict__ phases, long long S, int n_in) {
+                  float2 *__restrict__ phases, float2 *__restrict__ endph, long long S, int n_in) {
   const int c = order[blockIdx.x * 32 + threadIdx.x];
   if (c < 0) return;
   ClientDev *d = cl + c;
@@ -136,7 +136,9 @@ phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, Blk
   b.n_out = n_out;
   b.pad_ = 0;
   blk[c] = b;
-  d->phase = osc_chain_cf32<32>(d->phase, d->incr, phases + d->ph_off, n_out, d->renorm);
+  const float2 after = osc_chain_cf32<32>(d->phase, d->incr, phases + d->ph_off, n_out, d->renorm);
+  d->phase = after;
+  if (endph != nullptr) endph[c] = after;  // XLG_TRACK_STATE: the oscillator after this block, per client id
   d->hist = (S + n_in) - (first + (long long)n_out * D);  // src/xlating.c:76
 }
 

@@ -134,12 +134,17 @@ int main(int argc, char **argv) {
   for (int c = 0; c < n_clients; c++) outputs += clients[c].outputs;
   uint64_t batches = 0, calls = 0, shared = 0;
   xlg_dropin_stats(0, &batches, &calls, &shared); /* stays 0 with XLATING_B200_DROPIN=group */
+  uint64_t st[7] = {0, 0, 0, 0, 0, 0, 0};
+  xlg_dropin_stream_stats(0, st); /* the band's stream overlay (csrc/stream_overlay.h) */
   printf("{\"bench\": \"dropin_thread_per_client\", \"simd_status\": \"%s\", \"clients\": %d, \"blocks\": %d, \"window\": %d, "
          "\"seconds\": %.4f, \"input_msps\": %.2f, \"calls_per_s\": %.0f, \"us_per_call_per_thread\": %.1f, "
-         "\"outputs\": %llu, \"launch_batches\": %llu, \"engine_calls\": %llu, \"shared_inputs\": %llu}\n",
+         "\"outputs\": %llu, \"launch_batches\": %llu, \"engine_calls\": %llu, \"shared_inputs\": %llu, "
+         "\"stream_served\": %llu, \"stream_blocks\": %llu, \"stream_hits\": %llu, \"stream_desyncs\": %llu, "
+         "\"stream_joins\": %llu, \"stream_members\": %llu}\n",
          SIMD_STATUS, n_clients, n_blocks, g_window, dt, n_blocks * (BLOCK / 2) / dt / 1e6, (double)n_clients * n_blocks / dt,
          dt / n_blocks * 1e6, (unsigned long long)outputs, (unsigned long long)batches, (unsigned long long)calls,
-         (unsigned long long)shared);
+         (unsigned long long)shared, (unsigned long long)st[0], (unsigned long long)st[1], (unsigned long long)st[2],
+         (unsigned long long)st[3], (unsigned long long)st[4], (unsigned long long)st[6]);
   for (int c = 0; c < n_clients; c++) destroy_xlating(clients[c].filter);
   return 0;
 }
