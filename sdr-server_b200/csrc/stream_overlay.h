@@ -172,7 +172,7 @@ class AutoStream {
       const bool in_step = m.pos == h + 1 && m.run > 0;
       if (!in_step && n_members_.load() > 0) break;
       int64_t ticket = -1;
-      const int rc = publish(h + 1, h, input, bytes, fmt, elems, &ticket);
+      const int rc = publish(h + 1, h, input, bytes, fmt, elems, &ticket, /*bootstrap_only=*/!in_step);
       if (rc == 1) continue;  // raced with another publisher: look again
       if (rc < 0) break;
       m.run = in_step ? m.run + n : n;
@@ -270,11 +270,15 @@ class AutoStream {
 
   // Append block k = h+1.  0: published by this caller and complete; 1: head moved
   // (someone else published); <0: error, nothing published.
-  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, int64_t *ticket) {
+  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, int64_t *ticket,
+              bool bootstrap_only = false) {
     Entry *e = nullptr;
     {
       std::lock_guard<std::mutex> lk(mu_);
       if (head_.load() != h) return 1;
+      // a caller that is not in step may only start the log while the stream has no members
+      // (membership changes under this same lock, so the check cannot go stale)
+      if (bootstrap_only && n_members_.load() > 0) return -EBUSY;
       if (bytes > max_bytes_) return -EINVAL;
       e = &log_[(size_t)(k % ring_)];
       e->seq.store(-1);  // readers of the old block back off
