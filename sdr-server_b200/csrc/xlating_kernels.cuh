@@ -226,7 +226,7 @@ constexpr int T_UNROLL = XL_TILE_UNROLL;  // taps per unrolled inner-loop body (
 constexpr int T_CHUNK_F2 = T_JC * T_CG;       // float2 per chunk (1024)
 constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
 constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
-constexpr int T_MAX_CLASSES = 8;
+constexpr int T_MAX_CLASSES = 40;    // (D, T) classes per launch: 40 x 88 bytes stays inside the classic 4 KiB parameter space
 constexpr int T_RK_LONG = 4;         // outputs per thread in the long-filter kernel
 
 // Shape of the tile a CTA computes.  LO = number of output lanes in a warp, RK =
@@ -280,6 +280,20 @@ struct TileLaunch {
   int pad_;
   TileClass cls[T_MAX_CLASSES];
 };
+static_assert(sizeof(TileLaunch) <= 4000, "TileLaunch is passed as a __grid_constant__ kernel parameter");
+
+// class of CTA `bid`: the last class whose cta_begin <= bid (classes are laid out in launch order)
+__device__ __forceinline__ int class_of_cta(const TileLaunch &P, int bid) {
+  int lo = 0, hi = P.n_classes - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.cls[mid].cta_begin <= bid)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -338,8 +352,7 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   const int cbase = warp * S::kWarpClients + h * T_RC;  // first of this thread's 8 clients in the group
 
   // which class / client group / output tile is this CTA?
-  int ci = 0;
-  while (ci + 1 < P.n_classes && (int)blockIdx.x >= P.cls[ci + 1].cta_begin) ci++;
+  const int ci = class_of_cta(P, (int)blockIdx.x);
   const TileClass &K = P.cls[ci];
   const int local = (int)blockIdx.x - K.cta_begin;
   const int grp = local / K.tiles;
@@ -596,8 +609,7 @@ fir_long_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   const int o = lane & 15, h = lane >> 4;
   const int cbase = warp * 16 + h * T_RC;
 
-  int ci = 0;
-  while (ci + 1 < P.n_classes && (int)blockIdx.x >= P.cls[ci + 1].cta_begin) ci++;
+  const int ci = class_of_cta(P, (int)blockIdx.x);
   const TileClass &K = P.cls[ci];
   const int local = (int)blockIdx.x - K.cta_begin;
   const int seg = local % K.nseg;

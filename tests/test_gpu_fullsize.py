@@ -227,3 +227,29 @@ def test_long_filter_split_k_margin_64_clients(pkg):
         closer += e_gpu <= e_ref + 2e-7
     assert closer == 4, "the split-K sum should be at least as close to exact math as the sequential fp32 sum"
     g.close()
+
+
+def test_twenty_distinct_classes_all_on_the_tiled_kernel(pkg):
+    """sdr-server accepts any client rate that divides the band rate (src/tcp_server.c:101):
+    20 different (decimation, taps) classes of 8 clients each in ONE launch -- the class
+    table holds 40 -- every client on the tiled kernel, every client against the oracle."""
+    rng = np.random.default_rng(137)
+    fs, max_in = 2016000, 65536
+    rates = [48000, 96000, 24000, 32000, 16000, 8000, 12000, 56000, 72000, 28000,
+             36000, 18000, 14400, 9600, 42000, 63000, 84000, 126000, 144000, 168000]
+    assert all(fs % r == 0 for r in rates) and len(set(fs // r for r in rates)) == 20
+    plan = []
+    for r in rates:
+        for c in range(8):
+            center = int(-fs / 2 + r / 2 + (len(plan) + 0.5) * (fs - r) / 160)
+            plan.append({"rate": r, "decimation": fs // r, "center": center, "cutoff": r // 2, "tw": r // 5})
+    g, ids, oracles, tapsets = build(pkg, fs, max_in, plan)
+    assert len(tapsets) == 20
+    blocks = [rand_block(rng, "cu8", max_in) for _ in range(3)]
+    refs = oracle_stream(oracles, "cu8", blocks)
+    for b, x in enumerate(blocks):
+        t = g.submit("cu8", x)
+        g.wait(t)
+        check_all(g, t, ids, refs, b, "20 classes")
+    assert all(g.client_info(c)[1] == 1 for c in ids)
+    g.close()

@@ -34,3 +34,30 @@ def test_reference_arm_only_rank0(tmp_path):
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0
     assert r.stdout.strip() == ""
+
+
+def test_client_sharding_covers_every_client_once():
+    """BASELINE configs[4] partitioning (bench.shard_clients: client c -> rank c mod N): the
+    shards are disjoint, cover all 4096 clients and differ in size by at most one."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for world in (1, 2, 3, 4, 8):
+        shards = [bench.shard_clients(4096, r, world) for r in range(world)]
+        flat = sorted(c for s in shards for c in s)
+        assert flat == list(range(4096))
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1
+        assert all(c % world == r for r, s in enumerate(shards) for c in s)
+
+
+def test_sharded_clients_over_gloo_equal_the_unsharded_oracle(tmp_path):
+    """Host logic of the broadcast path with 2 gloo ranks: rank 0 broadcasts each block, every
+    rank runs the ORACLE for its shard; gathered, the shards' outputs are exactly what one
+    process computes for all clients (nothing is lost or duplicated by the partitioning)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29593", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29593",
+           os.path.join(ROOT, "tests", "_gloo_worker.py"), str(tmp_path), "broadcast"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.load(open(tmp_path / "broadcast.json"))
+    assert res["clients_checked"] == 12 and res["bit_identical"] is True
