@@ -240,6 +240,10 @@ class AutoStream {
   static void futex_wait(std::atomic<int> *w, int expected) {
     syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAIT_PRIVATE, expected, nullptr, nullptr, 0);
   }
+  static void futex_wait_us(std::atomic<int> *w, int expected, long us) {
+    struct timespec ts = {us / 1000000, (us % 1000000) * 1000};
+    syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAIT_PRIVATE, expected, &ts, nullptr, 0);
+  }
   static void futex_wake_all(std::atomic<int> *w) {
     syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
   }
@@ -274,7 +278,15 @@ class AutoStream {
               bool bootstrap_only = false) {
     Entry *e = nullptr;
     {
-      std::lock_guard<std::mutex> lk(mu_);
+      // When an SDR block lands, every dsp thread arrives here within microseconds with the
+      // same new block.  One publishes; the others must NOT queue up on the mutex (255 hand-
+      // offs of a contended lock, each a futex round trip, cost milliseconds per block): they
+      // sleep until the head moves and then take the lock-free reader path.
+      std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
+      if (!lk.owns_lock()) {
+        if (head_word_.load(std::memory_order_acquire) == (int)h) futex_wait_us(&head_word_, (int)h, 200);
+        return 1;
+      }
       if (head_.load() != h) return 1;
       // a caller that is not in step may only start the log while the stream has no members
       // (membership changes under this same lock, so the check cannot go stale)
@@ -297,6 +309,8 @@ class AutoStream {
       e->ticket = t;
       e->seq.store(k, std::memory_order_release);
       head_.store(k, std::memory_order_release);
+      head_word_.store((int)k, std::memory_order_release);
+      futex_wake_all(&head_word_);
       published_.fetch_add(1, std::memory_order_relaxed);
       *ticket = t;
     }
@@ -314,6 +328,7 @@ class AutoStream {
   std::vector<Entry> log_;
   std::mutex mu_;  // serialises publishers and membership changes (= all group mutations)
   std::atomic<int64_t> head_{-1};
+  std::atomic<int> head_word_{-1};  // low bits of head_, the futex word followers of a publisher sleep on
   std::atomic<int> n_members_{0};
   std::atomic<uint64_t> published_{0}, hits_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
 };

@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -213,6 +214,11 @@ struct xlg_group {
   bool have_last_conv = false;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
+  // guards the HostOut metadata (n_out / out_off / hist_after) against xlg_submit recycling an
+  // entry: held for tens of nanoseconds.  xlg_copy_output is called by every consumer thread of
+  // every block at the same moment (they are all woken by one completion): a sleeping mutex
+  // there turns into a convoy of futex hand-offs.
+  std::atomic_flag meta_lock = ATOMIC_FLAG_INIT;
   bool profiling = false;
   xlg_profile prof;
   uint64_t host_submit_ns = 0, host_wait_ns = 0, host_count_base = 0;
@@ -222,6 +228,24 @@ struct xlg_group {
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
+struct MetaLock {
+  std::atomic_flag &f;
+  explicit MetaLock(std::atomic_flag &flag) : f(flag) {
+    int spins = 0;
+    while (f.test_and_set(std::memory_order_acquire)) {
+      if (++spins < 256) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+      } else {
+        sched_yield();  // the holder may have been preempted
+        spins = 0;
+      }
+    }
+  }
+  ~MetaLock() { f.clear(std::memory_order_release); }
+};
+
 static size_t next_pow2(size_t v) {
   size_t p = 1;
   while (p < v) p <<= 1;
@@ -358,18 +382,21 @@ static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
       }
     }
     for (HostOut &h : g->ring_out) {
+      float2 *n_out = nullptr;
+      short2 *n_qout = nullptr;
+      if (!dev_out) {
+        CU_OK(cudaHostAlloc(&n_out, cap * sizeof(float2), cudaHostAllocDefault));
+        if (g->q_alloc) CU_OK(cudaHostAlloc(&n_qout, cap * sizeof(short2), cudaHostAllocDefault));
+      }
       std::lock_guard<std::mutex> lk(g->mu);
+      MetaLock ml(g->meta_lock);
       h.ticket.store(-1);  // resized: older results are gone
       // a consumer thread may still be writing an old result to its socket: the old
       // pinned arenas are retired, not freed, until the group is destroyed
       if (h.h_out) g->retired_host.push_back(h.h_out);
       if (h.h_qout) g->retired_host.push_back(h.h_qout);
-      h.h_out = nullptr;
-      h.h_qout = nullptr;
-      if (!dev_out) {
-        CU_OK(cudaHostAlloc(&h.h_out, cap * sizeof(float2), cudaHostAllocDefault));
-        if (g->q_alloc) CU_OK(cudaHostAlloc(&h.h_qout, cap * sizeof(short2), cudaHostAllocDefault));
-      }
+      h.h_out = n_out;
+      h.h_qout = n_qout;
     }
     g->arena_cap = cap;
   }
@@ -731,10 +758,12 @@ static int rebuild_layout(xlg_group *g) {
     const size_t want = std::max<size_t>((size_t)nc * 2, 64);
     for (HostOut &h : g->ring_out) {
       if (h.endph_cap >= (size_t)std::max(nc, 1)) continue;
+      float2 *fresh = nullptr;
+      CU_OK(cudaHostAlloc(&fresh, want * sizeof(float2), cudaHostAllocDefault));
       std::lock_guard<std::mutex> lk(g->mu);
+      MetaLock ml(g->meta_lock);
       if (h.h_endph) g->retired_host.push_back(h.h_endph);  // a reader may still hold the old array
-      h.h_endph = nullptr;
-      CU_OK(cudaHostAlloc(&h.h_endph, want * sizeof(float2), cudaHostAllocDefault));
+      h.h_endph = fresh;
       h.endph_cap = want;
     }
   }
@@ -759,13 +788,17 @@ static void partition_create(xlg_group *g, int device) {
     return;
   }
   cudaFree(0);  // make sure the primary context exists
+  // SMs asked for the oscillator partition: the driver rounds up to its granularity (8 on
+  // sm_90/sm_100 so far); XLATING_B200_PART_SMS asks for another count (measurement switch)
+  int want_sms = 8;
+  if (getenv("XLATING_B200_PART_SMS") != nullptr) want_sms = std::min(std::max(atoi(getenv("XLATING_B200_PART_SMS")), 1), 64);
   CUdevice dev;
   CUdevResource all, small, rest;
   unsigned int groups = 1;
   CUdevResourceDesc d_small = nullptr, d_rest = nullptr;
   CUstream st_ph = nullptr, st_c[xlg_group::kMaxCs] = {nullptr, nullptr, nullptr, nullptr};
   if (p_devget(&dev, device) != CUDA_SUCCESS || p_getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
-      p_split(&small, &groups, &all, &rest, 0, 8) != CUDA_SUCCESS || groups != 1 ||
+      p_split(&small, &groups, &all, &rest, 0, (unsigned)want_sms) != CUDA_SUCCESS || groups != 1 ||
       p_desc(&d_small, &small, 1) != CUDA_SUCCESS || p_desc(&d_rest, &rest, 1) != CUDA_SUCCESS ||
       p_create(&g->part.small_ctx, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
       p_create(&g->part.big_ctx, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
@@ -1102,8 +1135,9 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   // host mirror of the per-client output counts (same integer formula as the
   // oscillator pre-pass kernel)
   {
-    // consumers read this entry's metadata under the same mutex (xlg_output)
+    // consumers read this entry's metadata under the same mutex (xlg_output) / spinlock (xlg_copy_output)
     std::lock_guard<std::mutex> lk(g->mu);
+    MetaLock ml(g->meta_lock);
     ho.ticket.store(-1);  // the entry is being recycled
     ho.n_out.assign(g->clients.size(), 0);
     ho.out_off.assign(g->clients.size(), 0);
@@ -1447,7 +1481,7 @@ extern "C" int xlg_copy_output(xlg_group *g, int64_t ticket, int client_id, void
   const float2 *endph = nullptr;
   bool q15 = false;
   {
-    std::lock_guard<std::mutex> lk(g->mu);
+    MetaLock ml(g->meta_lock);
     if (ho.ticket.load() != ticket) return -ESTALE;
     if (client_id < 0 || client_id >= (int)ho.n_out.size()) return -EINVAL;
     n = (size_t)ho.n_out[client_id];
