@@ -327,6 +327,14 @@ def shard_clients(n_clients, rank, world):
     return list(range(rank, n_clients, world))
 
 
+ORIG_AFFINITY = None  # set by numa_bind; numa_unbind restores it for the CPU legs (they use every core)
+
+
+def numa_unbind():
+    if ORIG_AFFINITY is not None:
+        os.sched_setaffinity(0, ORIG_AFFINITY)
+
+
 def numa_bind(local_rank):
     """Bind this rank (and therefore its pinned allocations, first-touch) to the CPUs of its
     GPU's NUMA node: eight ranks writing D2H results into one node's DRAM was what bent the
@@ -345,6 +353,9 @@ def numa_bind(local_rank):
                             cpus |= set(range(int(a), int(b or a) + 1))
                         cpus &= os.sched_getaffinity(0)
                         if cpus:
+                            global ORIG_AFFINITY
+                            if ORIG_AFFINITY is None:
+                                ORIG_AFFINITY = os.sched_getaffinity(0)
                             os.sched_setaffinity(0, cpus)
                             return f"rank bound to CPUs {c} (GPU{local_rank}'s NUMA node)"
     except Exception:  # noqa: BLE001
@@ -773,7 +784,9 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ GPU arm
-    numa = numa_bind(local_rank) if world > 1 else None
+    # pinned host buffers are first-touched by this process: keep it (and them) on the GPU's NUMA node --
+    # a run that happens to start on the far socket loses a third of its D2H bandwidth (752 -> 527 MS/s e2e)
+    numa = numa_bind(local_rank)
     import torch
     import torch.distributed as dist
 
@@ -907,6 +920,7 @@ def main():
                        "block_latency_us": main_leg["block_latency_us"], "host": main_leg["host"], "numa": numa}}
     if legs:
         line["legs"] = legs
+    numa_unbind()  # the CPU legs below are entitled to every host core
     if not args.no_cpu and world == 1:
         try:
             line["cpu_baseline"] = cpu_arm(wl, blocks=320, warmup_blocks=16)

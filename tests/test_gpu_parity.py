@@ -657,3 +657,40 @@ def test_group_mixed_alignment_classes(pkg):
     hist = sorted({g.client_info(c)[0] for c in ids})
     assert len(hist) >= 4                         # several different alignments are live
     g.close()
+
+
+def test_group_speculative_prepass_hits_and_rollbacks(pkg):
+    """The oscillator pre-pass of block t+1 is launched with block t for "the same length
+    again" (csrc/xlating_group.cu).  Right guesses, wrong lengths, a Q15 block in between
+    (the two paths share history_offset, src/xlating.c:29), a client joining and one leaving
+    between blocks: every output must still be the reference's."""
+    rng = np.random.default_rng(89)
+    fs, max_in = 2016000, 32768
+    plan = pkg.client_plan(fs, [48000 if c % 2 == 0 else 96000 for c in range(20)], tw=None)
+    g, ids, oracles = make_group(pkg, fs, max_in, plan)
+    script = [("cf32", max_in), ("cf32", max_in), ("cf32", max_in), ("q15", max_in), ("cf32", max_in),
+              ("cf32", 10000), ("cf32", 10000), ("add", 0), ("cf32", 10000), ("cf32", max_in), ("remove", 0),
+              ("cf32", max_in), ("cf32", max_in), ("q15", 2000), ("q15", 2000), ("cf32", max_in), ("cf32", max_in)]
+    for step, (what, n) in enumerate(script):
+        if what == "add":
+            p = {"rate": 48000, "decimation": 42, "center": 4321, "cutoff": 24000, "tw": 9600}
+            taps = pkg.create_low_pass_filter(1.0, fs, p["cutoff"], p["tw"])
+            ids.append(g.add_client(p["decimation"], taps, p["center"]))
+            oracles.append(po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in))
+            continue
+        if what == "remove":
+            g.remove_client(ids.pop(3))
+            oracles.pop(3)
+            continue
+        x = rand_block(rng, "cu8", n)
+        if what == "q15":
+            t = g.submit("cu8", x, flags=pkg.XLG_PATH_Q15)
+            g.wait(t)
+            for cid, o in zip(ids, oracles):
+                np.testing.assert_array_equal(g.output(t, cid, q15=True), o.process_q15("cu8", x), err_msg=f"step {step}")
+        else:
+            t = g.submit("cu8", x)
+            g.wait(t)
+            for cid, o in zip(ids, oracles):
+                assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"step {step} client {cid}")
+    g.close()
