@@ -181,6 +181,11 @@ int xlg_dropin_stats(int device, uint64_t *batches, uint64_t *calls, uint64_t *s
  * [2] calls that found their block already published, [3] filters that fell out of step and left a group,
  * [4] filters that joined one, [5] private calls whose block was in the log, [6] filters that are members now. */
 int xlg_dropin_stream_stats(int device, uint64_t *stats7);
+/* Where the served calls' time went, nanoseconds summed over all calling threads: ns7[0] whole calls served by a
+ * group, [1] copying the caller's row out of the result ring, [2] comparing the caller's bytes with the log
+ * entry, [3] sleeping until the block's results were readable, and for the publishing callers [4] copying the
+ * block into the log, [5] the group submit, [6] waiting for the GPU. */
+int xlg_dropin_stream_times(int device, uint64_t *ns7);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <sys/syscall.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -89,7 +90,16 @@ class AutoStream {
   };
   struct Stats {
     uint64_t published, hits, desyncs, joins, private_matches;
+    // where the callers' time goes (nanoseconds, summed over all threads): comparing a call's bytes
+    // with the log entry; sleeping until the block's results are readable; and, for publishers, the
+    // copy into the log, the group submit and the wait for the GPU
+    uint64_t ns_compare, ns_wait, ns_pub_copy, ns_pub_submit, ns_pub_wait;
   };
+  static uint64_t now_ns() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+  }
 
   AutoStream(const StreamOps &ops, int ring, size_t max_block_bytes)
       : ops_(ops), ring_(ring < 4 ? 4 : ring), max_bytes_(max_block_bytes), log_((size_t)(ring < 4 ? 4 : ring)) {}
@@ -113,8 +123,14 @@ class AutoStream {
       const int64_t h = head_.load(std::memory_order_acquire);
       if (k <= h) {
         Entry &e = log_[(size_t)(k % ring_)];
-        if (!matches(e, k, input, bytes, fmt)) break;  // recycled or different bytes: desync
-        if (!wait_done(e, k)) break;
+        const uint64_t t0 = now_ns();
+        const bool same = matches(e, k, input, bytes, fmt);
+        const uint64_t t1 = now_ns();
+        ns_compare_.fetch_add(t1 - t0, std::memory_order_relaxed);
+        if (!same) break;  // recycled or different bytes: desync
+        const bool ready = wait_done(e, k);
+        ns_wait_.fetch_add(now_ns() - t1, std::memory_order_relaxed);
+        if (!ready) break;
         const int64_t ticket = e.ticket;
         std::atomic_thread_fence(std::memory_order_acquire);
         if (e.seq.load() != k) break;
@@ -219,7 +235,8 @@ class AutoStream {
   }
 
   Stats stats() const {
-    return Stats{published_.load(), hits_.load(), desyncs_.load(), joins_.load(), private_matches_.load()};
+    return Stats{published_.load(), hits_.load(),     desyncs_.load(),    joins_.load(),         private_matches_.load(),
+                 ns_compare_.load(), ns_wait_.load(), ns_pub_copy_.load(), ns_pub_submit_.load(), ns_pub_wait_.load()};
   }
 
  private:
@@ -298,13 +315,17 @@ class AutoStream {
         e->host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
         if (e->host == nullptr) return -ENOMEM;
       }
+      const uint64_t t0 = now_ns();
       memcpy(e->host, input, bytes);
       e->key = bytes > 0 ? block_key(input, bytes) : 0;
+      const uint64_t t1 = now_ns();
+      ns_pub_copy_.fetch_add(t1 - t0, std::memory_order_relaxed);
       e->bytes = bytes;
       e->fmt = fmt;
       e->done.store(done_tag(k));
       int64_t t = -1;
       const int rc = ops_.submit(ops_.ctx, fmt, e->host, elems, &t);
+      ns_pub_submit_.fetch_add(now_ns() - t1, std::memory_order_relaxed);
       if (rc != 0) return rc < 0 ? rc : -EIO;  // entry stays invalid (seq = -1), head unchanged
       e->ticket = t;
       e->seq.store(k, std::memory_order_release);
@@ -315,7 +336,9 @@ class AutoStream {
       *ticket = t;
     }
     // outside the lock: the next block can be published while this one computes
+    const uint64_t tw = now_ns();
     const int rc = ops_.wait(ops_.ctx, *ticket);
+    ns_pub_wait_.fetch_add(now_ns() - tw, std::memory_order_relaxed);
     int pending = done_tag(k);
     e->done.compare_exchange_strong(pending, done_tag(k) | (rc == 0 ? 1 : 2));  // fails if the entry was recycled
     futex_wake_all(&e->done);
@@ -331,6 +354,7 @@ class AutoStream {
   std::atomic<int> head_word_{-1};  // low bits of head_, the futex word followers of a publisher sleep on
   std::atomic<int> n_members_{0};
   std::atomic<uint64_t> published_{0}, hits_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
+  std::atomic<uint64_t> ns_compare_{0}, ns_wait_{0}, ns_pub_copy_{0}, ns_pub_submit_{0}, ns_pub_wait_{0};
 };
 
 }  // namespace xl

@@ -158,6 +158,7 @@ struct Engine {
   int stream_ring = 64;      // XLATING_B200_STREAM_RING
   std::vector<StreamHost *> streams;  // guarded by mu
   std::atomic<uint64_t> stream_served{0};
+  std::atomic<uint64_t> stream_copy_ns{0}, stream_call_ns{0};  // time in xlg_copy_output / in whole served calls
 };
 constexpr size_t kPoolMaxBytes = (size_t)2 << 30;  // device + pinned bytes kept for reuse
 
@@ -729,6 +730,7 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
   if (as != nullptr) {
     const size_t elems = (size_t)n * 2;
     AutoStream::Served sv;
+    const uint64_t t_call = AutoStream::now_ns();
     if (f->as_m.member && as->member_call(f->as_m, input, bytes, fmt, elems, &sv) == 1) {
       // the group computed this block for every member; take this filter's row and state
       const long long first = f->S - f->hist;
@@ -736,7 +738,9 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
       size_t want = 0, got = 0;
       if (last_ok >= first) want = (size_t)((last_ok - first) / (long long)f->D) + 1;
       xlg_client_state st;
+      const uint64_t t_copy = AutoStream::now_ns();
       const int rc = xlg_copy_output(f->sh->g, sv.ticket, sv.client, f->h_out, (size_t)f->out_cap, &got, &st);
+      e->stream_copy_ns.fetch_add(AutoStream::now_ns() - t_copy, std::memory_order_relaxed);
       if (rc == 0 && got == want) {
         f->hist = st.hist;
         f->ph_re = st.phase_re;
@@ -745,6 +749,7 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
         f->S += n;
         f->dev_stale = true;
         e->stream_served.fetch_add(1, std::memory_order_relaxed);
+        e->stream_call_ns.fetch_add(AutoStream::now_ns() - t_call, std::memory_order_relaxed);
         *output_len = got;
         return;
       }
@@ -870,6 +875,28 @@ int xlg_dropin_stats(int device, uint64_t *batches, uint64_t *calls, uint64_t *s
   uint64_t hits = 0, publishes = 0;
   it->second->cache->stats(&hits, &publishes);
   if (shared_inputs != NULL) *shared_inputs = hits;
+  return 0;
+}
+
+int xlg_dropin_stream_times(int device, uint64_t *ns7) {
+  std::lock_guard<std::mutex> lk(g_engines_mu);
+  auto it = g_engines.find(device);
+  if (it == g_engines.end() || ns7 == NULL) return -ENOENT;
+  Engine *e = it->second;
+  memset(ns7, 0, 7 * sizeof(uint64_t));
+  ns7[0] = e->stream_call_ns.load();
+  ns7[1] = e->stream_copy_ns.load();
+  std::lock_guard<std::mutex> lk2(e->mu);
+  for (StreamHost *sh : e->streams) {
+    AutoStream *as = sh->as.load();
+    if (as == nullptr) continue;
+    const AutoStream::Stats st = as->stats();
+    ns7[2] += st.ns_compare;
+    ns7[3] += st.ns_wait;
+    ns7[4] += st.ns_pub_copy;
+    ns7[5] += st.ns_pub_submit;
+    ns7[6] += st.ns_pub_wait;
+  }
   return 0;
 }
 

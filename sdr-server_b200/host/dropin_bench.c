@@ -136,6 +136,13 @@ int main(int argc, char **argv) {
   xlg_dropin_stats(0, &batches, &calls, &shared); /* stays 0 with XLATING_B200_DROPIN=group */
   uint64_t st[7] = {0, 0, 0, 0, 0, 0, 0};
   xlg_dropin_stream_stats(0, st); /* the band's stream overlay (csrc/stream_overlay.h) */
+  uint64_t ns[7] = {0, 0, 0, 0, 0, 0, 0};
+  xlg_dropin_stream_times(0, ns);
+  if (st[0] > 0 && st[1] > 0)
+    fprintf(stderr, "overlay: per served call %.1f us (compare %.1f, wait for the block %.1f, copy out %.1f); per published "
+                    "block: copy %.1f us, submit %.1f us, wait GPU %.1f us\n",
+            ns[0] / 1e3 / st[0], ns[2] / 1e3 / st[0], ns[3] / 1e3 / st[0], ns[1] / 1e3 / st[0], ns[4] / 1e3 / st[1],
+            ns[5] / 1e3 / st[1], ns[6] / 1e3 / st[1]);
   printf("{\"bench\": \"dropin_thread_per_client\", \"simd_status\": \"%s\", \"clients\": %d, \"blocks\": %d, \"window\": %d, "
          "\"seconds\": %.4f, \"input_msps\": %.2f, \"calls_per_s\": %.0f, \"us_per_call_per_thread\": %.1f, "
          "\"outputs\": %llu, \"launch_batches\": %llu, \"engine_calls\": %llu, \"shared_inputs\": %llu, "
