@@ -36,6 +36,16 @@
  * to the ones it was given, computed from a state that consumed exactly the blocks the
  * filter consumed: results never depend on scheduling, only speed does.
  *
+ * Threads.  The callers are the reference's dsp threads -- hundreds of them, and whichever
+ * arrives first with a block publishes it, so the publisher is a different thread every
+ * time.  The group operations (CUDA calls behind StreamOps) are therefore NOT made by the
+ * callers: the first CUDA call of every new host thread costs milliseconds of per-thread
+ * runtime setup (measured: 2.5-3.2 ms per published block with 256 dsp threads).  Two
+ * service threads per stream make them: the SUBMITTER executes submit / add / remove
+ * requests strictly in the order they were queued (that order is what makes a joining
+ * filter part of exactly the blocks after the one it consumed last), the WAITER waits for
+ * each submitted block's ticket and wakes the callers sleeping on the log entry.
+ *
  * Publishing rule for private filters: only a filter that is "in step" (it consumed the
  * log's newest block) may append a block -- or anybody while the stream has no members
  * yet (bootstrap).  A filter fed by a different source can then never push a foreign
@@ -55,7 +65,10 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "block_cache.h"  // block_key()
@@ -102,8 +115,28 @@ class AutoStream {
   }
 
   AutoStream(const StreamOps &ops, int ring, size_t max_block_bytes)
-      : ops_(ops), ring_(ring < 4 ? 4 : ring), max_bytes_(max_block_bytes), log_((size_t)(ring < 4 ? 4 : ring)) {}
+      : ops_(ops), ring_(ring < 4 ? 4 : ring), max_bytes_(max_block_bytes), log_((size_t)(ring < 4 ? 4 : ring)) {
+    // the log's block copies are allocated here, by the creating thread, not lazily by whichever
+    // dsp thread publishes first (page-locking memory from a fresh thread costs milliseconds)
+    for (Entry &e : log_) e.host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
+    submitter_ = std::thread([this] { submitter_main(); });
+    waiter_ = std::thread([this] { waiter_main(); });
+  }
   ~AutoStream() {
+    {
+      std::lock_guard<std::mutex> lk(q_mu_);
+      Task t;
+      t.kind = Task::kStop;
+      tasks_.push_back(t);
+    }
+    q_cv_.notify_all();
+    submitter_.join();
+    {
+      std::lock_guard<std::mutex> lk(w_mu_);
+      waits_.push_back(Pending{-1, -1});
+    }
+    w_cv_.notify_all();
+    waiter_.join();
     for (Entry &e : log_)
       if (e.host != nullptr) ops_.free_block(ops_.ctx, e.host);
   }
@@ -119,12 +152,13 @@ class AutoStream {
   int member_call(Member &m, const void *input, size_t bytes, int fmt, size_t elems, Served *sv) {
     if (!m.member) return 0;
     const int64_t k = m.pos;
+    bool mine = false;  // this caller appended block k itself: its bytes ARE the entry's
     for (;;) {
       const int64_t h = head_.load(std::memory_order_acquire);
       if (k <= h) {
         Entry &e = log_[(size_t)(k % ring_)];
         const uint64_t t0 = now_ns();
-        const bool same = matches(e, k, input, bytes, fmt);
+        const bool same = mine ? e.seq.load(std::memory_order_acquire) == k : matches(e, k, input, bytes, fmt);
         const uint64_t t1 = now_ns();
         ns_compare_.fetch_add(t1 - t0, std::memory_order_relaxed);
         if (!same) break;  // recycled or different bytes: desync
@@ -142,15 +176,11 @@ class AutoStream {
         return 1;
       }
       // k == h + 1: nobody has brought this block yet
-      int64_t ticket = -1;
-      const int rc = publish(k, h, input, bytes, fmt, elems, &ticket);
-      if (rc == 1) continue;  // somebody else published meanwhile: compare with theirs
-      if (rc < 0) break;      // the group refused the block: serve it privately
-      sv->ticket = ticket;
-      sv->client = m.client;
-      m.pos = k + 1;
-      m.run += (int64_t)(elems / 2);
-      return 1;
+      const int rc = publish(k, h, input, bytes, fmt, elems);
+      if (rc < 0) break;  // the log cannot take the block: serve it privately
+      mine = rc == 0;
+      // rc == 0: published by this caller, rc == 1: by somebody else meanwhile -- either way the
+      // block is (being) computed for every member: compare and wait like everybody else
     }
     leave(m);
     desyncs_.fetch_add(1, std::memory_order_relaxed);
@@ -187,8 +217,7 @@ class AutoStream {
       // not in the log.  May this caller append it?
       const bool in_step = m.pos == h + 1 && m.run > 0;
       if (!in_step && n_members_.load() > 0) break;
-      int64_t ticket = -1;
-      const int rc = publish(h + 1, h, input, bytes, fmt, elems, &ticket, /*bootstrap_only=*/!in_step);
+      const int rc = publish(h + 1, h, input, bytes, fmt, elems, /*bootstrap_only=*/!in_step);
       if (rc == 1) continue;  // raced with another publisher: look again
       if (rc < 0) break;
       m.run = in_step ? m.run + n : n;
@@ -212,8 +241,14 @@ class AutoStream {
     if (m.run < needed_history && m.run != total_consumed) return false;
     std::lock_guard<std::mutex> lk(mu_);
     if (m.pos != head_.load() + 1) return false;  // not caught up: the newest block is not its last one
+    // queued behind every submit so far, and no block can be published while mu_ is held: the filter
+    // becomes a member of exactly the blocks after the one it consumed last
     int client = -1;
-    if (ops_.add(ops_.ctx, filter, m.run, &client) != 0) return false;
+    Task t;
+    t.kind = Task::kAdd;
+    t.filter = filter;
+    t.valid_history = m.run;
+    if (run_sync(t, &client) != 0) return false;
     m.member = true;
     m.client = client;
     n_members_.fetch_add(1);
@@ -225,7 +260,10 @@ class AutoStream {
   void leave(Member &m) {
     if (m.member) {
       std::lock_guard<std::mutex> lk(mu_);
-      ops_.remove(ops_.ctx, m.client);
+      Task t;
+      t.kind = Task::kRemove;
+      t.client = m.client;
+      enqueue(t);  // in order with the submits; nobody waits for it
       n_members_.fetch_sub(1);
     }
     m.member = false;
@@ -245,8 +283,9 @@ class AutoStream {
     uint64_t key = 0;
     size_t bytes = 0;
     int fmt = 0;
+    size_t elems = 0;
     void *host = nullptr;          // pinned copy of the block
-    int64_t ticket = -1;
+    int64_t ticket = -1;           // written by the submitter before the block is marked done
     // futex word: (log index << 2) | state, state 0 = pending, 1 = results readable, 2 = failed.
     // The index is part of the word because the thread that published block k may be
     // preempted between the GPU finishing and its store: by then the entry may hold
@@ -289,67 +328,159 @@ class AutoStream {
     }
   }
 
-  // Append block k = h+1.  0: published by this caller and complete; 1: head moved
-  // (someone else published); <0: error, nothing published.
-  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, int64_t *ticket,
-              bool bootstrap_only = false) {
-    Entry *e = nullptr;
-    {
-      // When an SDR block lands, every dsp thread arrives here within microseconds with the
-      // same new block.  One publishes; the others must NOT queue up on the mutex (255 hand-
-      // offs of a contended lock, each a futex round trip, cost milliseconds per block): they
-      // sleep until the head moves and then take the lock-free reader path.
-      std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
-      if (!lk.owns_lock()) {
-        if (head_word_.load(std::memory_order_acquire) == (int)h) futex_wait_us(&head_word_, (int)h, 200);
-        return 1;
-      }
-      if (head_.load() != h) return 1;
-      // a caller that is not in step may only start the log while the stream has no members
-      // (membership changes under this same lock, so the check cannot go stale)
-      if (bootstrap_only && n_members_.load() > 0) return -EBUSY;
-      if (bytes > max_bytes_) return -EINVAL;
-      e = &log_[(size_t)(k % ring_)];
-      e->seq.store(-1);  // readers of the old block back off
-      if (e->host == nullptr) {
-        e->host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
-        if (e->host == nullptr) return -ENOMEM;
-      }
-      const uint64_t t0 = now_ns();
-      memcpy(e->host, input, bytes);
-      e->key = bytes > 0 ? block_key(input, bytes) : 0;
-      const uint64_t t1 = now_ns();
-      ns_pub_copy_.fetch_add(t1 - t0, std::memory_order_relaxed);
-      e->bytes = bytes;
-      e->fmt = fmt;
-      e->done.store(done_tag(k));
-      int64_t t = -1;
-      const int rc = ops_.submit(ops_.ctx, fmt, e->host, elems, &t);
-      ns_pub_submit_.fetch_add(now_ns() - t1, std::memory_order_relaxed);
-      if (rc != 0) return rc < 0 ? rc : -EIO;  // entry stays invalid (seq = -1), head unchanged
-      e->ticket = t;
-      e->seq.store(k, std::memory_order_release);
-      head_.store(k, std::memory_order_release);
-      head_word_.store((int)k, std::memory_order_release);
-      futex_wake_all(&head_word_);
-      published_.fetch_add(1, std::memory_order_relaxed);
-      *ticket = t;
+  // Append block k = h+1 and queue its submission.  0: appended by this caller; 1: head moved
+  // (someone else appended); <0: error, nothing appended.
+  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, bool bootstrap_only = false) {
+    // When an SDR block lands, every dsp thread arrives here within microseconds with the
+    // same new block.  One appends it; the others must NOT queue up on the mutex (255 hand-
+    // offs of a contended lock, each a futex round trip, cost milliseconds per block): they
+    // sleep until the head moves and then take the lock-free reader path.
+    std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
+    if (!lk.owns_lock()) {
+      if (head_word_.load(std::memory_order_acquire) == (int)h) futex_wait_us(&head_word_, (int)h, 200);
+      return 1;
     }
-    // outside the lock: the next block can be published while this one computes
-    const uint64_t tw = now_ns();
-    const int rc = ops_.wait(ops_.ctx, *ticket);
-    ns_pub_wait_.fetch_add(now_ns() - tw, std::memory_order_relaxed);
+    if (head_.load() != h) return 1;
+    // a caller that is not in step may only start the log while the stream has no members
+    // (membership changes under this same lock, so the check cannot go stale)
+    if (bootstrap_only && n_members_.load() > 0) return -EBUSY;
+    if (bytes > max_bytes_) return -EINVAL;
+    Entry *e = &log_[(size_t)(k % ring_)];
+    e->seq.store(-1);  // readers of the old block back off
+    if (e->host == nullptr) {
+      e->host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
+      if (e->host == nullptr) return -ENOMEM;
+    }
+    const uint64_t t0 = now_ns();
+    memcpy(e->host, input, bytes);
+    e->key = bytes > 0 ? block_key(input, bytes) : 0;
+    ns_pub_copy_.fetch_add(now_ns() - t0, std::memory_order_relaxed);
+    e->bytes = bytes;
+    e->fmt = fmt;
+    e->elems = elems;
+    e->ticket = -1;
+    e->done.store(done_tag(k));
+    e->seq.store(k, std::memory_order_release);
+    head_.store(k, std::memory_order_release);
+    head_word_.store((int)k, std::memory_order_release);
+    Task t;
+    t.kind = Task::kSubmit;
+    t.k = k;
+    enqueue(t);
+    lk.unlock();
+    futex_wake_all(&head_word_);
+    published_.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+
+  // ---- service threads ----
+  struct Task {
+    enum { kSubmit, kAdd, kRemove, kStop } kind = kSubmit;
+    int64_t k = -1;            // kSubmit: log index
+    void *filter = nullptr;    // kAdd
+    int64_t valid_history = 0;
+    int client = -1;           // kRemove
+    int *out_client = nullptr; // kAdd: result
+    int *out_rc = nullptr;
+    std::atomic<int> *finished = nullptr;  // kAdd: futex word set to 1 when done
+  };
+  struct Pending {
+    int64_t k, ticket;
+  };
+
+  void enqueue(const Task &t) {
+    {
+      std::lock_guard<std::mutex> lk(q_mu_);
+      tasks_.push_back(t);
+    }
+    q_cv_.notify_one();
+  }
+  int run_sync(Task &t, int *client) {
+    int rc = -EIO;
+    std::atomic<int> fin{0};
+    t.out_client = client;
+    t.out_rc = &rc;
+    t.finished = &fin;
+    enqueue(t);
+    while (fin.load(std::memory_order_acquire) == 0) futex_wait_us(&fin, 0, 1000);
+    return rc;
+  }
+  void finish(Entry &e, int64_t k, bool ok) {
     int pending = done_tag(k);
-    e->done.compare_exchange_strong(pending, done_tag(k) | (rc == 0 ? 1 : 2));  // fails if the entry was recycled
-    futex_wake_all(&e->done);
-    return rc == 0 ? 0 : -EIO;
+    e.done.compare_exchange_strong(pending, done_tag(k) | (ok ? 1 : 2));  // fails if the entry was recycled
+    futex_wake_all(&e.done);
+  }
+  void submitter_main() {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(q_mu_);
+        // blocks arrive back to back while a stream runs: poll briefly before sleeping
+        for (int spin = 0; tasks_.empty() && spin < 2000; spin++) {
+          lk.unlock();
+#if defined(__x86_64__) || defined(__i386__)
+          __builtin_ia32_pause();
+#endif
+          lk.lock();
+        }
+        q_cv_.wait(lk, [this] { return !tasks_.empty(); });
+        t = tasks_.front();
+        tasks_.pop_front();
+      }
+      if (t.kind == Task::kStop) return;
+      if (t.kind == Task::kSubmit) {
+        Entry &e = log_[(size_t)(t.k % ring_)];
+        int64_t ticket = -1;
+        const uint64_t t0 = now_ns();
+        const int rc = ops_.submit(ops_.ctx, e.fmt, e.host, e.elems, &ticket);
+        ns_pub_submit_.fetch_add(now_ns() - t0, std::memory_order_relaxed);
+        if (rc != 0) {
+          finish(e, t.k, false);  // every member falls back to its private engine for this block
+          continue;
+        }
+        e.ticket = ticket;
+        {
+          std::lock_guard<std::mutex> lk(w_mu_);
+          waits_.push_back(Pending{t.k, ticket});
+        }
+        w_cv_.notify_one();
+      } else if (t.kind == Task::kAdd) {
+        *t.out_rc = ops_.add(ops_.ctx, t.filter, t.valid_history, t.out_client);
+        t.finished->store(1, std::memory_order_release);
+        futex_wake_all(t.finished);
+      } else {
+        ops_.remove(ops_.ctx, t.client);
+      }
+    }
+  }
+  void waiter_main() {
+    for (;;) {
+      Pending p;
+      {
+        std::unique_lock<std::mutex> lk(w_mu_);
+        w_cv_.wait(lk, [this] { return !waits_.empty(); });
+        p = waits_.front();
+        waits_.pop_front();
+      }
+      if (p.k < 0) return;
+      const uint64_t t0 = now_ns();
+      const int rc = ops_.wait(ops_.ctx, p.ticket);
+      ns_pub_wait_.fetch_add(now_ns() - t0, std::memory_order_relaxed);
+      finish(log_[(size_t)(p.k % ring_)], p.k, rc == 0);
+    }
   }
 
   const StreamOps ops_;
   const int ring_;
   const size_t max_bytes_;
   std::vector<Entry> log_;
-  std::mutex mu_;  // serialises publishers and membership changes (= all group mutations)
+  std::mutex mu_;  // serialises publishers and membership changes
+  // the service threads and their queues
+  std::mutex q_mu_, w_mu_;
+  std::condition_variable q_cv_, w_cv_;
+  std::deque<Task> tasks_;
+  std::deque<Pending> waits_;
+  std::thread submitter_, waiter_;
   std::atomic<int64_t> head_{-1};
   std::atomic<int> head_word_{-1};  // low bits of head_, the futex word followers of a publisher sleep on
   std::atomic<int> n_members_{0};

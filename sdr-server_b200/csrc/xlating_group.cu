@@ -141,14 +141,50 @@ static bool drv(const char *name, F *fn) {
 // the device pipeline is XLG_SLOTS deep, but results stay readable for host_ring
 // tickets so that a consumer thread blocked on a slow socket does not lose data
 // (the reference absorbs that with a 64-block queue per client, src/config.c:183).
+// Per-ticket metadata array that consumer threads read WITHOUT a lock (xlg_copy_output: the
+// entry's ticket is the sequence number of a seqlock -- xlg_submit sets it to -1 before it
+// touches the array and to the new ticket afterwards).  The storage only ever grows; an
+// outgrown array is retired, never freed while the group lives, so a reader that raced with
+// the growth still reads valid memory (and is then rejected by the ticket check).
+template <typename T>
+struct MetaArr {
+  std::atomic<T *> p{nullptr};
+  size_t cap = 0;
+  std::atomic<size_t> n{0};
+  std::vector<T *> *retired = nullptr;
+  MetaArr() = default;
+  MetaArr(const MetaArr &) : p(nullptr), cap(0), n(0), retired(nullptr) {}  // (vector<HostOut> construction only)
+  size_t size() const { return n.load(std::memory_order_relaxed); }
+  T &operator[](size_t i) { return p.load(std::memory_order_relaxed)[i]; }
+  T get(size_t i) const { return p.load(std::memory_order_acquire)[i]; }
+  void assign(size_t count, T value) {
+    if (count > cap) {
+      const size_t ncap = std::max<size_t>(count * 2, 64);
+      T *fresh = new T[ncap];
+      T *old = p.load();
+      if (old != nullptr && retired != nullptr) retired->push_back(old);
+      p.store(fresh, std::memory_order_release);
+      cap = ncap;
+    }
+    T *a = p.load();
+    for (size_t i = 0; i < count; i++) a[i] = value;
+    n.store(count, std::memory_order_release);
+  }
+  void release() {
+    delete[] p.load();
+    p.store(nullptr);
+    cap = 0;
+  }
+};
+
 struct HostOut {
   std::atomic<int64_t> ticket{-1};
   bool q15 = false;
   float2 *h_out = nullptr;   // pinned; nullptr for XLG_OUT_DEVICE groups
   short2 *h_qout = nullptr;
-  std::vector<int> n_out;    // per client id
-  std::vector<int> out_off;  // per client id
-  std::vector<long long> hist_after;  // XLG_TRACK_STATE: per client id, history_offset after this ticket
+  MetaArr<int> n_out;    // per client id
+  MetaArr<int> out_off;  // per client id
+  MetaArr<long long> hist_after;  // XLG_TRACK_STATE: per client id, history_offset after this ticket
   float2 *h_endph = nullptr;          // XLG_TRACK_STATE: pinned, oscillator after this ticket, per client id
   size_t endph_cap = 0;
 };
@@ -189,7 +225,7 @@ struct xlg_group {
   // submit is what was guessed, its pre-pass is already done -- a lone block then takes
   // convert + FIR instead of 49 us of dependent chain + FIR; otherwise the table is restored
   // and the pre-pass runs as before.  XLATING_B200_SPECULATE=0 turns it off.
-  ClientDev *d_clients_backup = nullptr;
+  SpecSave *d_clients_backup = nullptr;  // (hist, oscillator) of every client before the speculative pre-pass
   bool speculate = true;
   bool spec_valid = false;
   long long spec_S = 0;
@@ -200,6 +236,7 @@ struct xlg_group {
   short2 *d_qtaps = nullptr;
   void *d_tile_taps = nullptr;
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
+  int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long2, default) or 64 (XLATING_B200_LONG=1)
   int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
   int *d_member_cid = nullptr;      // client id per member slot (-1 = padding)
@@ -220,6 +257,8 @@ struct xlg_group {
   Slot slots[XLG_SLOTS];
   std::vector<HostOut> ring_out;  // indexed by ticket % ring_out.size()
   std::vector<void *> retired_host;
+  std::vector<int *> retired_meta_i;        // outgrown MetaArr storage (see MetaArr)
+  std::vector<long long *> retired_meta_ll;
   long long *d_trace = nullptr;  // XLATING_B200_TRACE=1: per-CTA timeline of the tiled kernel
   int trace_ctas = 0;
   std::atomic<int64_t> next_ticket{0};
@@ -227,11 +266,6 @@ struct xlg_group {
   bool have_last_conv = false;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
-  // guards the HostOut metadata (n_out / out_off / hist_after) against xlg_submit recycling an
-  // entry: held for tens of nanoseconds.  xlg_copy_output is called by every consumer thread of
-  // every block at the same moment (they are all woken by one completion): a sleeping mutex
-  // there turns into a convoy of futex hand-offs.
-  std::atomic_flag meta_lock = ATOMIC_FLAG_INIT;
   bool profiling = false;
   xlg_profile prof;
   uint64_t host_submit_ns = 0, host_wait_ns = 0, host_count_base = 0;
@@ -241,23 +275,6 @@ struct xlg_group {
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
-struct MetaLock {
-  std::atomic_flag &f;
-  explicit MetaLock(std::atomic_flag &flag) : f(flag) {
-    int spins = 0;
-    while (f.test_and_set(std::memory_order_acquire)) {
-      if (++spins < 256) {
-#if defined(__x86_64__) || defined(__i386__)
-        __builtin_ia32_pause();
-#endif
-      } else {
-        sched_yield();  // the holder may have been preempted
-        spins = 0;
-      }
-    }
-  }
-  ~MetaLock() { f.clear(std::memory_order_release); }
-};
 
 static size_t next_pow2(size_t v) {
   size_t p = 1;
@@ -402,7 +419,6 @@ static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
         if (g->q_alloc) CU_OK(cudaHostAlloc(&n_qout, cap * sizeof(short2), cudaHostAllocDefault));
       }
       std::lock_guard<std::mutex> lk(g->mu);
-      MetaLock ml(g->meta_lock);
       h.ticket.store(-1);  // resized: older results are gone
       // a consumer thread may still be writing an old result to its socket: the old
       // pinned arenas are retired, not freed, until the group is destroyed
@@ -633,6 +649,35 @@ static int rebuild_layout(xlg_group *g) {
                      cudaMemcpyHostToDevice));
   }
 
+  // 3a. long filters: every 256 KiB block streams ALL their taps once (each tap serves only ~52
+  //     outputs of a block), 63 MB for BASELINE configs[4]'s 512 clients per GPU -- they fit the
+  //     126 MB L2, but the partial sums and the ring evict them between launches (measured: 64 MB of
+  //     DRAM reads per launch, profiles/r1_fir_long_summary.txt).  Pin them: a persisting access-
+  //     policy window over the packed taps on the compute streams.
+  if (!g->long_classes.empty() && !tile_taps.empty() && getenv("XLATING_B200_NO_L2PIN") == nullptr) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, g->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+        prop.accessPolicyMaxWindowSize > 0) {
+      const size_t bytes = tile_taps.size() * sizeof(float2);
+      const size_t carve = std::min(bytes, (size_t)prop.persistingL2CacheMaxSize);
+      const size_t window = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = g->d_tile_taps;
+      attr.accessPolicyWindow.num_bytes = window;
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      bool ok = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess;
+      for (int i = 0; i < xlg_group::kMaxCs && ok; i++)
+        ok = cudaStreamSetAttribute(g->s_cs[i], cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+      if (!ok) {
+        cudaGetLastError();
+        XL_LOG("could not pin the long filters' taps in L2 (continuing without)");
+      }
+    }
+  }
+
   // 3b. oscillator-table order: tile classes (the order the tiled kernel walks them),
   //     then generic clients; 32 clients per table group
   {
@@ -690,7 +735,8 @@ static int rebuild_layout(xlg_group *g) {
       for (TileClassHost &ch : g->long_classes) {
         int cap = 0;
         for (int id : ch.real) cap = std::max(cap, g->clients[id].out_cap);
-        const size_t kpad_max = ((size_t)cap + W_KT - 1) / W_KT * W_KT;
+        const size_t kt = (size_t)g->long_kt;
+        const size_t kpad_max = ((size_t)cap + kt - 1) / kt * kt;
         ch.k.part_off = (long long)part;
         ch.k.kpad = (int)kpad_max;
         part += (size_t)ch.k.nseg * ch.k.n_groups * kpad_max * T_CG;
@@ -755,7 +801,7 @@ static int rebuild_layout(xlg_group *g) {
     CU_OK(cudaMemset(g->d_clients, 0, g->d_clients_cap * sizeof(ClientDev)));
     if (g->d_clients_backup) cudaFree(g->d_clients_backup);
     g->d_clients_backup = nullptr;
-    CU_OK(cudaMalloc(&g->d_clients_backup, g->d_clients_cap * sizeof(ClientDev)));
+    CU_OK(cudaMalloc(&g->d_clients_backup, g->d_clients_cap * sizeof(SpecSave)));
   }
   if (nc > 0) CU_OK(cudaMemcpy(g->d_clients, tab.data(), (size_t)nc * sizeof(ClientDev), cudaMemcpyHostToDevice));
 
@@ -776,8 +822,8 @@ static int rebuild_layout(xlg_group *g) {
       if (h.endph_cap >= (size_t)std::max(nc, 1)) continue;
       float2 *fresh = nullptr;
       CU_OK(cudaHostAlloc(&fresh, want * sizeof(float2), cudaHostAllocDefault));
+      if (h.h_endph != nullptr) memcpy(fresh, h.h_endph, h.endph_cap * sizeof(float2));  // tickets in the ring stay readable
       std::lock_guard<std::mutex> lk(g->mu);
-      MetaLock ml(g->meta_lock);
       if (h.h_endph) g->retired_host.push_back(h.h_endph);  // a reader may still hold the old array
       h.h_endph = fresh;
       h.endph_cap = want;
@@ -873,6 +919,11 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
   g->max_input_len = max_input_len;
   g->flags = flags;
   g->ring_out = std::vector<HostOut>(host_ring);
+  for (HostOut &h : g->ring_out) {
+    h.n_out.retired = &g->retired_meta_i;
+    h.out_off.retired = &g->retired_meta_i;
+    h.hist_after.retired = &g->retired_meta_ll;
+  }
   int rc = 0;
   auto fail = [&](int code) {
     xlg_destroy(g);
@@ -907,6 +958,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
   {
     const char *tv = getenv("XLATING_B200_TILE");
     if (tv != nullptr) g->tile_force = atoi(tv);
+    const char *lv = getenv("XLATING_B200_LONG");
+    if (lv != nullptr && atoi(lv) == 1) g->long_kt = W_KT;  // the first long-filter kernel (A/B)
     const char *sv = getenv("XLATING_B200_SPECULATE");
     if (sv != nullptr) g->speculate = atoi(sv) != 0;
     const char *cv = getenv("XLATING_B200_CSTREAMS");
@@ -921,7 +974,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
           cudaSuccess ||
       cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fir_long2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM) != cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
@@ -984,7 +1038,12 @@ extern "C" void xlg_destroy(xlg_group *g) {
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_qout) cudaFreeHost(h.h_qout);
     if (h.h_endph) cudaFreeHost(h.h_endph);
+    h.n_out.release();
+    h.out_off.release();
+    h.hist_after.release();
   }
+  for (int *p : g->retired_meta_i) delete[] p;
+  for (long long *p : g->retired_meta_ll) delete[] p;
   for (void *p : g->retired_host) cudaFreeHost(p);
   if (g->ev_t0) cudaEventDestroy(g->ev_t0);
   if (g->ev_t1) cudaEventDestroy(g->ev_t1);
@@ -1130,8 +1189,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     const bool hit = g->spec_valid && !q15 && !g->dirty && !g->profiling && g->spec_ticket == t_next &&
                      g->spec_S == g->S && g->spec_n == (int)(input_len / 2);
     if (g->spec_valid && !hit) {
-      CU_OK(cudaMemcpyAsync(g->d_clients, g->d_clients_backup, (size_t)g->max_client * sizeof(ClientDev),
-                            cudaMemcpyDeviceToDevice, g->s_ph));
+      restore_clients_kernel<<<(g->max_client + 127) / 128, 128, 0, g->s_ph>>>(g->d_clients, g->d_clients_backup,
+                                                                              g->max_client);
       g->spec_valid = false;
       g->spec_misses++;
     }
@@ -1169,8 +1228,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   {
     // consumers read this entry's metadata under the same mutex (xlg_output) / spinlock (xlg_copy_output)
     std::lock_guard<std::mutex> lk(g->mu);
-    MetaLock ml(g->meta_lock);
-    ho.ticket.store(-1);  // the entry is being recycled
+    ho.ticket.store(-1);  // the entry is being recycled (seqlock write-begin for lock-free readers)
+    std::atomic_thread_fence(std::memory_order_seq_cst);
     ho.n_out.assign(g->clients.size(), 0);
     ho.out_off.assign(g->clients.size(), 0);
     if (g->flags & XLG_TRACK_STATE) ho.hist_after.assign(g->clients.size(), 0);
@@ -1268,7 +1327,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       g->spec_hits++;
     } else {
       phase_cf32_kernel<<<g->n_order / 32, P_THREADS, 0, g->s_ph>>>(g->d_clients, g->d_order, s.d_blk, s.d_phases,
-                                                                   s.d_endph, S, n);
+                                                                   s.d_endph, nullptr, S, n);
     }
     if (g->profiling) CU_OK(cudaEventRecord(s.pf[3], g->s_ph));
     if (!ran_ahead) CU_OK(cudaEventRecord(s.ev_phase, g->s_ph));
@@ -1277,10 +1336,9 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     if (!q15 && g->speculate && !g->profiling && n > 0 && g->n_order > 0 && g->d_clients_backup != nullptr) {
       Slot &ns = g->slots[(ticket + 1) % XLG_SLOTS];
       if (ns.ticket.load() >= 0) CU_OK(cudaStreamWaitEvent(g->s_ph, ns.ev_done, 0));  // its tables are still in use
-      CU_OK(cudaMemcpyAsync(g->d_clients_backup, g->d_clients, (size_t)nc * sizeof(ClientDev), cudaMemcpyDeviceToDevice,
-                            g->s_ph));
+      // (the kernel itself saves every client's state before it advances it: no copy on the critical path)
       phase_cf32_kernel<<<g->n_order / 32, P_THREADS, 0, g->s_ph>>>(g->d_clients, g->d_order, ns.d_blk, ns.d_phases,
-                                                                   ns.d_endph, S + n, n);
+                                                                   ns.d_endph, g->d_clients_backup, S + n, n);
       CU_OK(cudaEventRecord(ns.ev_phase, g->s_ph));
       g->spec_valid = true;
       g->spec_S = S + n;
@@ -1387,21 +1445,25 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       TileClass k = ch.k;
       k.first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
       k.n_out = n_out;
-      k.tiles = (n_out + W_KT - 1) / W_KT;
+      k.tiles = (n_out + g->long_kt - 1) / g->long_kt;
       k.cta_begin = ctas;
       ctas += k.nseg * k.tiles * k.n_groups;
       max_out = std::max(max_out, n_out);
       max_groups = std::max(max_groups, k.n_groups);
       P.cls[P.n_classes++] = k;
-      s.tile_macs += (uint64_t)k.tiles * W_KT * (uint64_t)k.L * (uint64_t)ch.members.size();
+      s.tile_macs += (uint64_t)k.tiles * g->long_kt * (uint64_t)k.L * (uint64_t)ch.members.size();
     }
     if (ctas > 0) {
       if (g->profiling) {
         CU_OK(cudaEventRecord(s.pf[8], cs));
         s.pf_long = true;
       }
-      fir_long_cf32_kernel<<<ctas, W_THREADS, W_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
-                                                           s.d_partial);
+      if (g->long_kt == W2_KT)
+        fir_long2_cf32_kernel<<<ctas, W2_THREADS, W2_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
+                                                                s.d_partial);
+      else
+        fir_long_cf32_kernel<<<ctas, W_THREADS, W_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
+                                                             s.d_partial);
       dim3 rgrid((max_out + 7) / 8, max_groups, P.n_classes);
       fir_long_reduce_kernel<<<rgrid, 256, 0, cs>>>(P, s.d_partial, g->d_members, g->d_member_incr, s.d_phases,
                                                     s.d_out);
@@ -1535,18 +1597,25 @@ extern "C" int xlg_copy_output(xlg_group *g, int64_t ticket, int client_id, void
   const float2 *endph = nullptr;
   bool q15 = false;
   {
-    MetaLock ml(g->meta_lock);
-    if (ho.ticket.load() != ticket) return -ESTALE;
+    // lock-free: every consumer thread of a block arrives here at the same moment
+    if (ho.ticket.load(std::memory_order_acquire) != ticket) return -ESTALE;
     if (client_id < 0 || client_id >= (int)ho.n_out.size()) return -EINVAL;
-    n = (size_t)ho.n_out[client_id];
+    n = (size_t)ho.n_out.get((size_t)client_id);
     q15 = ho.q15;
-    src = q15 ? (const void *)(ho.h_qout + ho.out_off[client_id]) : (const void *)(ho.h_out + ho.out_off[client_id]);
+    const int off = ho.out_off.get((size_t)client_id);
+    float2 *const h_out = *(float2 *volatile *)&ho.h_out;
+    short2 *const h_qout = *(short2 *volatile *)&ho.h_qout;
+    src = q15 ? (const void *)(h_qout + off) : (const void *)(h_out + off);
     if (state_after != nullptr) {
-      if (!(g->flags & XLG_TRACK_STATE) || q15 || ho.h_endph == nullptr || client_id >= (int)ho.hist_after.size())
+      float2 *const h_endph = *(float2 *volatile *)&ho.h_endph;
+      if (!(g->flags & XLG_TRACK_STATE) || q15 || h_endph == nullptr || client_id >= (int)ho.hist_after.size())
         return -EINVAL;
-      hist_after = ho.hist_after[client_id];
-      endph = ho.h_endph + client_id;
+      hist_after = ho.hist_after.get((size_t)client_id);
+      endph = h_endph + client_id;
     }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (ho.ticket.load() != ticket) return -ESTALE;  // recycled while we looked: nothing above can be trusted
+    if (src == nullptr || n > g->arena_cap) return -ESTALE;
   }
   if (out_len) *out_len = n;
   memcpy(dst, src, std::min(n, cap) * (q15 ? sizeof(short2) : sizeof(float2)));

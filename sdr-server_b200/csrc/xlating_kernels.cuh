@@ -62,6 +62,11 @@ struct ClientDev {
   int ph_off;             // cf32 oscillator table: phase of EVEN output k lives at phases[ph_off + 32*(k/2)]
 };
 
+struct SpecSave {
+  long long hist;
+  float2 phase;
+};
+
 // ---------------------------------------------------------------------------
 // convert: raw interleaved I,Q scalars -> ring  (src/xlating.c:389-390, 399-400,
 // 409-410 for cf32; :418, :425, :432 for Q15).  All conversions are exact.
@@ -123,11 +128,16 @@ constexpr int P_QTHREADS = 64;  // Q15 variant (one thread per client)
 // because a lone warp can only keep ~32 stores in flight.)
 __global__ void __launch_bounds__(P_THREADS)
 phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, BlkInfo *__restrict__ blk,
-                  float2 *__restrict__ phases, float2 *__restrict__ endph, long long S, int n_in) {
+                  float2 *__restrict__ phases, float2 *__restrict__ endph, SpecSave *__restrict__ save, long long S,
+                  int n_in) {
   const int c = order[blockIdx.x * 32 + threadIdx.x];
   if (c < 0) return;
   ClientDev *d = cl + c;
   if (!d->active) return;
+  if (save != nullptr) {  // a speculative run (the next block's pre-pass, launched early): keep what it overwrites
+    save[c].hist = d->hist;
+    save[c].phase = d->phase;
+  }
   const int D = d->D;
   const long long first = S - d->hist;
   const int n_out = outputs_of_call(first, S, n_in, d->T, D, d->out_cap);
@@ -140,6 +150,14 @@ phase_cf32_kernel(ClientDev *__restrict__ cl, const int *__restrict__ order, Blk
   d->phase = after;
   if (endph != nullptr) endph[c] = after;  // XLG_TRACK_STATE: the oscillator after this block, per client id
   d->hist = (S + n_in) - (first + (long long)n_out * D);  // src/xlating.c:76
+}
+
+// undo a speculative pre-pass that guessed the wrong block length
+__global__ void restore_clients_kernel(ClientDev *__restrict__ cl, const SpecSave *__restrict__ save, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n || !cl[c].active) return;
+  cl[c].hist = save[c].hist;
+  cl[c].phase = save[c].phase;
 }
 
 __global__ void __launch_bounds__(P_QTHREADS)
@@ -701,6 +719,170 @@ fir_long_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
 #pragma unroll
     for (int i = 0; i < T_RK_LONG; i++) {
       float4 *row = reinterpret_cast<float4 *>(pp + (size_t)(o + 16 * i) * T_CG);
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++)
+        row[q] = make_float4(acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// long filters, second generation (the default): the same split-K scheme with
+//   * 4 warps per CTA that split the CTA's 128-tap segment four ways (32 taps each) and
+//     add their partial sums through shared memory in a fixed order -- two CTAs = 8 warps
+//     per SM instead of 4 (the first kernel's one warp per scheduler left the FMA pipe
+//     52 % busy, profiles/r1_fir_long_summary.txt);
+//   * a 56-output tile (8 output lanes x 7 outputs per thread; lane = (client octet,
+//     output column), a warp covers all 32 clients): BASELINE configs[4] produces 51-52
+//     outputs per 256 KiB block, which wasted 19 % of a 64-output tile and wastes 7 % of
+//     this one; per tap a thread issues 7 + 4 shared loads for 224 FFMA (8 for 128 before).
+// Partial sums, the reduction kernel and the arithmetic are unchanged (the order of the
+// fp32 additions inside a segment differs: four 32-tap runs instead of one 128-tap run).
+// ---------------------------------------------------------------------------
+constexpr int W2_LO = 8;               // output lanes per warp
+constexpr int W2_RK = 7;               // outputs per thread
+constexpr int W2_KT = W2_LO * W2_RK;   // 56 outputs per CTA
+constexpr int W2_WARPS = 4;
+constexpr int W2_THREADS = 32 * W2_WARPS;
+constexpr int W2_JW = W_JS / W2_WARPS;  // taps per warp (32)
+constexpr int W2_SMEM = W_JS * T_CG * 8 + 64 + W2_KT * W_JSP * 8;  // 32 KiB taps + barrier + 57 KiB strips
+static_assert((W2_WARPS - 1) * 32 * W2_RK * T_RC * 2 * 4 <= W2_KT * W_JSP * 8, "reduction scratch reuses the strips");
+
+__global__ void __launch_bounds__(W2_THREADS, 2)
+fir_long2_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
+                      const float2 *__restrict__ tile_taps, float2 *__restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2 *ts = reinterpret_cast<float2 *>(smem);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + W_JS * T_CG * 8);
+  float2 *xs = reinterpret_cast<float2 *>(smem + W_JS * T_CG * 8 + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o = lane & (W2_LO - 1), h = lane / W2_LO;  // output column, client octet
+  const int cbase = h * T_RC;
+
+  const int ci = class_of_cta(P, (int)blockIdx.x);
+  const TileClass &K = P.cls[ci];
+  const int local = (int)blockIdx.x - K.cta_begin;
+  const int seg = local % K.nseg;
+  const int rest = local / K.nseg;
+  const int tile = rest % K.tiles;
+  const int grp = rest / K.tiles;
+  const int k0 = tile * W2_KT;
+  const int f0 = seg * W_JS;
+  const int len = min(W_JS, K.L - f0);  // multiple of 8
+  const int D = K.D;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long w0 = K.first + (long long)k0 * D + f0;  // first sample of strip 0
+  const bool aligned = ((K.first | (long long)D) & 1) == 0;  // f0 and k0*D are even then
+  const unsigned strip_bytes = (unsigned)len * 8u;
+  if (tid == 0) {
+    const unsigned tap_bytes = (unsigned)len * T_CG * 8u;
+    mbar_expect_tx(bar, tap_bytes + (aligned ? W2_KT * strip_bytes : 0u));
+    tma_bulk_g2s(ts, tile_taps + K.taps_off + ((long long)grp * K.L + f0) * T_CG, tap_bytes, bar);
+  }
+  __syncthreads();  // expect_tx is posted before any strip copy can complete
+  if (aligned) {
+    if (tid < W2_KT) {  // one strip per thread: x[(k0 + tid)*D + f0 .. + len), contiguous in the ring
+      const unsigned idx = (unsigned)((unsigned long long)(w0 + (long long)tid * D)) & mask;
+      const unsigned n1 = min((unsigned)len, mask + 1u - idx);
+      tma_bulk_g2s(xs + tid * W_JSP, ring + idx, n1 * 8u, bar);
+      if (n1 < (unsigned)len) tma_bulk_g2s(xs + tid * W_JSP + n1, ring, ((unsigned)len - n1) * 8u, bar);
+    }
+  } else {
+    for (int e = tid; e < W2_KT * W_JS; e += W2_THREADS) {
+      const int k = e / W_JS, f = e - k * W_JS;
+      if (f < len) {
+        const long long ab = w0 + (long long)k * D + f;
+        cp_async_8(xs + k * W_JSP + f, ring + ((unsigned)((unsigned long long)ab) & mask));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  mbar_wait(bar, 0);
+
+  float2 acc[W2_RK][T_RC];
+#pragma unroll
+  for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+  const float2 *xb[W2_RK];
+#pragma unroll
+  for (int i = 0; i < W2_RK; i++) xb[i] = xs + (o + W2_LO * i) * W_JSP;
+  const float4 *tp = reinterpret_cast<const float4 *>(ts + cbase);
+
+  const bool group_active = grp * T_CG < K.n_members;
+  const int f_end = min(len, (warp + 1) * W2_JW);
+  if (group_active) {
+#pragma unroll 1
+    for (int f = warp * W2_JW; f < f_end; f += T_UNROLL) {
+#pragma unroll
+      for (int u = 0; u < T_UNROLL; u++) {
+        float2 x[W2_RK];
+        float4 tq[T_RC / 2];
+#pragma unroll
+        for (int i = 0; i < W2_RK; i++) x[i] = xb[i][f + u];
+#pragma unroll
+        for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+        for (int i = 0; i < W2_RK; i++) {
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) {
+            float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+            a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+            a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+            a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+            a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+            a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+            a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+            a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+            a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+          }
+        }
+      }
+    }
+  }
+  // warps 1..3 hand their sums to warp 0 through shared memory (the strips are no longer needed);
+  // layout [warp-1][value][lane]: conflict-free both ways, fixed order of addition
+  __syncthreads();
+  float *red = reinterpret_cast<float *>(xs);
+  constexpr int NV = W2_RK * T_RC * 2;  // floats per thread
+  if (warp > 0 && group_active) {
+    float *dst = red + (size_t)(warp - 1) * NV * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+      for (int c = 0; c < T_RC; c++) {
+        dst[(size_t)((i * T_RC + c) * 2) * 32] = acc[i][c].x;
+        dst[(size_t)((i * T_RC + c) * 2 + 1) * 32] = acc[i][c].y;
+      }
+  }
+  __syncthreads();
+  if (warp == 0 && group_active) {
+#pragma unroll
+    for (int w = 0; w < W2_WARPS - 1; w++) {
+      const float *src = red + (size_t)w * NV * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+        for (int c = 0; c < T_RC; c++) {
+          acc[i][c].x += src[(size_t)((i * T_RC + c) * 2) * 32];
+          acc[i][c].y += src[(size_t)((i * T_RC + c) * 2 + 1) * 32];
+        }
+    }
+    // partial sums: [segment][group][output][32 clients]
+    float2 *pp = partial + K.part_off + (((long long)seg * K.n_groups + grp) * K.kpad + k0) * T_CG + cbase;
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++) {
+      float4 *row = reinterpret_cast<float4 *>(pp + (size_t)(o + W2_LO * i) * T_CG);
 #pragma unroll
       for (int q = 0; q < T_RC / 2; q++)
         row[q] = make_float4(acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y);
