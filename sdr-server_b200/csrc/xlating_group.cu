@@ -236,7 +236,8 @@ struct xlg_group {
   short2 *d_qtaps = nullptr;
   void *d_tile_taps = nullptr;
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
-  int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long2, default) or 64 (XLATING_B200_LONG=1)
+  int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long3 / fir_long2) or 64 (XLATING_B200_LONG=1)
+  int long_gen = 3;       // XLATING_B200_LONG=1|2|3: which long-filter kernel (3 = pipelined, the default)
   int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
   int *d_member_cid = nullptr;      // client id per member slot (-1 = padding)
@@ -739,7 +740,7 @@ static int rebuild_layout(xlg_group *g) {
         const size_t kpad_max = ((size_t)cap + kt - 1) / kt * kt;
         ch.k.part_off = (long long)part;
         ch.k.kpad = (int)kpad_max;
-        part += (size_t)ch.k.nseg * ch.k.n_groups * kpad_max * T_CG;
+        part += (size_t)ch.k.nseg * ch.k.n_groups * kpad_max * T_CG;  // (the pipelined kernel uses ksplit <= nseg slabs of it)
       }
       if (part > g->partial_cap) {
         g->partial_cap = part;
@@ -959,7 +960,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     const char *tv = getenv("XLATING_B200_TILE");
     if (tv != nullptr) g->tile_force = atoi(tv);
     const char *lv = getenv("XLATING_B200_LONG");
-    if (lv != nullptr && atoi(lv) == 1) g->long_kt = W_KT;  // the first long-filter kernel (A/B)
+    if (lv != nullptr && atoi(lv) >= 1 && atoi(lv) <= 3) g->long_gen = atoi(lv);  // A/B of the long-filter kernels
+    if (g->long_gen == 1) g->long_kt = W_KT;
     const char *sv = getenv("XLATING_B200_SPECULATE");
     if (sv != nullptr) g->speculate = atoi(sv) != 0;
     const char *cv = getenv("XLATING_B200_CSTREAMS");
@@ -975,7 +977,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
       cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
       cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(fir_long2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(fir_long2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fir_long3_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM) != cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
@@ -1438,6 +1441,18 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     TileLaunch P;
     memset(&P, 0, sizeof(P));
     int ctas = 0, max_out = 0, max_groups = 0;
+    // the pipelined kernel needs 16-byte aligned strips (even decimation and window start) for its TMA
+    // bulk copies; fir_long2 takes over otherwise (it can fall back to 8-byte cp.async)
+    bool pipelined = g->long_gen == 3;
+    for (TileClassHost &ch : g->long_classes) {
+      const HostClient &h0 = g->clients[ch.real[0]];
+      const int n_out = ho.n_out[ch.real[0]];
+      if (n_out <= 0) continue;
+      const long long first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
+      if (((first | (long long)h0.D) & 1) != 0) pipelined = false;
+    }
+    int n_live = 0;
+    for (TileClassHost &ch : g->long_classes) n_live += ho.n_out[ch.real[0]] > 0 ? 1 : 0;
     for (TileClassHost &ch : g->long_classes) {
       const HostClient &h0 = g->clients[ch.real[0]];
       const int n_out = ho.n_out[ch.real[0]];
@@ -1447,7 +1462,20 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       k.n_out = n_out;
       k.tiles = (n_out + g->long_kt - 1) / g->long_kt;
       k.cta_begin = ctas;
-      ctas += k.nseg * k.tiles * k.n_groups;
+      k.nslab = k.nseg;
+      k.ksplit = k.nseg;
+      k.seg_per = 1;
+      if (pipelined) {
+        // one resident CTA per SM: as many CTAs along the tap axis as fill one wave of this class's share
+        const int share = std::max(1, g->fir_sms / std::max(n_live, 1));
+        const int want = std::max(1, share / std::max(1, k.tiles * k.n_groups));
+        k.seg_per = (k.nseg + std::min(want, k.nseg) - 1) / std::min(want, k.nseg);
+        k.ksplit = (k.nseg + k.seg_per - 1) / k.seg_per;
+        k.nslab = k.ksplit;
+        ctas += k.ksplit * k.tiles * k.n_groups;
+      } else {
+        ctas += k.nseg * k.tiles * k.n_groups;
+      }
       max_out = std::max(max_out, n_out);
       max_groups = std::max(max_groups, k.n_groups);
       P.cls[P.n_classes++] = k;
@@ -1458,7 +1486,10 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
         CU_OK(cudaEventRecord(s.pf[8], cs));
         s.pf_long = true;
       }
-      if (g->long_kt == W2_KT)
+      if (pipelined)
+        fir_long3_cf32_kernel<<<ctas, W3_THREADS, W3_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
+                                                                s.d_partial);
+      else if (g->long_kt == W2_KT)
         fir_long2_cf32_kernel<<<ctas, W2_THREADS, W2_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
                                                                 s.d_partial);
       else

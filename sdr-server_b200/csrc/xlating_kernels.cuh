@@ -244,7 +244,7 @@ constexpr int T_UNROLL = XL_TILE_UNROLL;  // taps per unrolled inner-loop body (
 constexpr int T_CHUNK_F2 = T_JC * T_CG;       // float2 per chunk (1024)
 constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
 constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
-constexpr int T_MAX_CLASSES = 40;    // (D, T) classes per launch: 40 x 88 bytes stays inside the classic 4 KiB parameter space
+constexpr int T_MAX_CLASSES = 36;    // (D, T) classes per launch: 36 x 104 bytes stays inside the classic 4 KiB parameter space
 constexpr int T_RK_LONG = 4;         // outputs per thread in the long-filter kernel
 
 // Shape of the tile a CTA computes.  LO = number of output lanes in a warp, RK =
@@ -291,6 +291,10 @@ struct TileClass {
   long long part_off;  // float2 offset of this class in the partial-sum buffer
   int nseg;            // tap segments of W_JS flat taps
   int kpad;            // outputs rounded up to the tile size (row count of the partial buffer)
+  int nslab;           // partial-sum slabs the reduction adds: nseg, or ksplit for the pipelined kernel
+  int ksplit;          // pipelined long-filter kernel: CTAs along the tap axis per (group, tile)
+  int seg_per;         // ... and consecutive segments each of them walks
+  int pad2_;
 };
 
 struct TileLaunch {
@@ -890,6 +894,176 @@ fir_long2_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// long filters, pipelined (the default when the strips are 16-byte aligned): ONE resident CTA
+// per SM walks `seg_per` consecutive 128-tap segments of one (group, 56-output tile) through a
+// two-stage ring -- while its 8 warps (16 taps of the segment each, all 32 clients x 56 outputs)
+// accumulate segment i, warp 0 has already issued the TMA bulk copies of segment i+1 (57 copies:
+// the taps and one strip per output row).  Against fir_long2: no idle time while a CTA loads
+// (there the two CTAs of an SM were often both waiting), the prologue and the cross-warp
+// reduction are paid once per ~13 segments instead of once per segment, and the partial-sum
+// slabs shrink from one per segment (121 for BASELINE configs[4]) to one per CTA along the tap
+// axis (9): the reduction kernel and its traffic shrink with them.
+// ---------------------------------------------------------------------------
+constexpr int W3_WARPS = 8;
+constexpr int W3_THREADS = 32 * W3_WARPS;
+constexpr int W3_STAGES = 2;
+constexpr int W3_JW = W_JS / W3_WARPS;                       // taps per warp per segment (16)
+constexpr int W3_STAGE_BYTES = W_JS * T_CG * 8 + W2_KT * W_JSP * 8;  // 32 KiB taps + 57 KiB strips
+constexpr int W3_SMEM = W3_STAGES * W3_STAGE_BYTES + 64;
+static_assert((W3_WARPS - 1) * 32 * W2_RK * T_RC * 2 * 4 <= W3_STAGES * W3_STAGE_BYTES, "reduction scratch reuses the stages");
+
+__global__ void __launch_bounds__(W3_THREADS, 1)
+fir_long3_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
+                      const float2 *__restrict__ tile_taps, float2 *__restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W3_STAGES * W3_STAGE_BYTES);  // full[2], empty[2]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o = lane & (W2_LO - 1), h = lane / W2_LO;  // output column, client octet
+  const int cbase = h * T_RC;
+
+  const int ci = class_of_cta(P, (int)blockIdx.x);
+  const TileClass &K = P.cls[ci];
+  const int local = (int)blockIdx.x - K.cta_begin;
+  const int sp = local % K.ksplit;
+  const int rest = local / K.ksplit;
+  const int tile = rest % K.tiles;
+  const int grp = rest / K.tiles;
+  const int k0 = tile * W2_KT;
+  const int D = K.D;
+  const int seg_begin = sp * K.seg_per;
+  const int seg_end = min(seg_begin + K.seg_per, K.nseg);
+  const bool group_active = grp * T_CG < K.n_members;
+
+  if (tid == 0) {
+    for (int st = 0; st < W3_STAGES; st++) {
+      mbar_init(&bars[st], 1);
+      mbar_init(&bars[W3_STAGES + st], W3_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // warp 0 is also the producer: lane 0 announces the stage's bytes, then every lane issues
+  // its copies (strip rows lane and lane + 32, lane 0 also the taps)
+  auto load_segment = [&](int sg, int st) {
+    const int f0 = sg * W_JS;
+    const int len = min(W_JS, K.L - f0);
+    float2 *ts = reinterpret_cast<float2 *>(smem + st * W3_STAGE_BYTES);
+    float2 *xs = ts + W_JS * T_CG;
+    const unsigned strip_bytes = (unsigned)len * 8u, tap_bytes = (unsigned)len * T_CG * 8u;
+    if (lane == 0) {
+      mbar_expect_tx(&bars[st], tap_bytes + W2_KT * strip_bytes);
+      tma_bulk_g2s(ts, tile_taps + K.taps_off + ((long long)grp * K.L + f0) * T_CG, tap_bytes, &bars[st]);
+    }
+    __syncwarp();
+    const long long w0 = K.first + (long long)k0 * D + f0;
+    for (int r = lane; r < W2_KT; r += 32) {
+      const unsigned idx = (unsigned)((unsigned long long)(w0 + (long long)r * D)) & mask;
+      const unsigned n1 = min((unsigned)len, mask + 1u - idx);
+      tma_bulk_g2s(xs + r * W_JSP, ring + idx, n1 * 8u, &bars[st]);
+      if (n1 < (unsigned)len) tma_bulk_g2s(xs + r * W_JSP + n1, ring, ((unsigned)len - n1) * 8u, &bars[st]);
+    }
+  };
+
+  float2 acc[W2_RK][T_RC];
+#pragma unroll
+  for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+
+  if (group_active && seg_begin < seg_end) {
+    if (warp == 0) load_segment(seg_begin, 0);
+    for (int sg = seg_begin; sg < seg_end; sg++) {
+      const int it = sg - seg_begin, st = it % W3_STAGES;
+      if (warp == 0 && sg + 1 < seg_end) {
+        // the other stage held segment sg-1: every warp has released it before entering segment sg
+        // (or is about to); refill it with segment sg+1 while segment sg is being accumulated
+        const int ns = (it + 1) % W3_STAGES;
+        if (it >= 1) mbar_wait(&bars[W3_STAGES + ns], (unsigned)(((it - 1) / W3_STAGES) & 1));
+        load_segment(sg + 1, ns);
+      }
+      mbar_wait(&bars[st], (unsigned)((it / W3_STAGES) & 1));
+      const int len = min(W_JS, K.L - sg * W_JS);
+      const float2 *ts = reinterpret_cast<const float2 *>(smem + st * W3_STAGE_BYTES);
+      const float2 *xs = ts + W_JS * T_CG;
+      const float4 *tp = reinterpret_cast<const float4 *>(ts + cbase);
+      const float2 *xb[W2_RK];
+#pragma unroll
+      for (int i = 0; i < W2_RK; i++) xb[i] = xs + (o + W2_LO * i) * W_JSP;
+      const int f_end = min(len, (warp + 1) * W3_JW);
+#pragma unroll 1
+      for (int f = warp * W3_JW; f < f_end; f += T_UNROLL) {
+#pragma unroll
+        for (int u = 0; u < T_UNROLL; u++) {
+          float2 x[W2_RK];
+          float4 tq[T_RC / 2];
+#pragma unroll
+          for (int i = 0; i < W2_RK; i++) x[i] = xb[i][f + u];
+#pragma unroll
+          for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+          for (int i = 0; i < W2_RK; i++) {
+#pragma unroll
+            for (int q = 0; q < T_RC / 2; q++) {
+              float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+              a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+              a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+              a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+              a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+              a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+              a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+              a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+              a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[W3_STAGES + st]);  // this warp is done with the stage
+    }
+  }
+  // warps 1..7 hand their sums to warp 0 through shared memory, layout [warp-1][value][lane]
+  __syncthreads();
+  float *red = reinterpret_cast<float *>(smem);
+  constexpr int NV = W2_RK * T_RC * 2;
+  if (warp > 0 && group_active) {
+    float *dst = red + (size_t)(warp - 1) * NV * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+      for (int c = 0; c < T_RC; c++) {
+        dst[(size_t)((i * T_RC + c) * 2) * 32] = acc[i][c].x;
+        dst[(size_t)((i * T_RC + c) * 2 + 1) * 32] = acc[i][c].y;
+      }
+  }
+  __syncthreads();
+  if (warp == 0 && group_active) {
+#pragma unroll 1
+    for (int w = 0; w < W3_WARPS - 1; w++) {
+      const float *src = red + (size_t)w * NV * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+        for (int c = 0; c < T_RC; c++) {
+          acc[i][c].x += src[(size_t)((i * T_RC + c) * 2) * 32];
+          acc[i][c].y += src[(size_t)((i * T_RC + c) * 2 + 1) * 32];
+        }
+    }
+    // partial sums: [tap split][group][output][32 clients]
+    float2 *pp = partial + K.part_off + (((long long)sp * K.n_groups + grp) * K.kpad + k0) * T_CG + cbase;
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++) {
+      float4 *row = reinterpret_cast<float4 *>(pp + (size_t)(o + W2_LO * i) * T_CG);
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++)
+        row[q] = make_float4(acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y);
+    }
+  }
+}
+
 // Adds the segments in order, derotates, stores.  Block = 32 clients (lanes) x 8 outputs.
 __global__ void __launch_bounds__(256)
 fir_long_reduce_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ partial,
@@ -911,7 +1085,7 @@ fir_long_reduce_kernel(const __grid_constant__ TileLaunch P, const float2 *__res
   // loads in batches of 8 (independent, so their L2 latencies overlap); the additions
   // stay strictly in segment order
   int s = 0;
-  for (; s + 8 <= K.nseg; s += 8) {
+  for (; s + 8 <= K.nslab; s += 8) {
     float2 v[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) v[u] = pp[(size_t)(s + u) * seg_stride];
@@ -921,7 +1095,7 @@ fir_long_reduce_kernel(const __grid_constant__ TileLaunch P, const float2 *__res
       acc.y += v[u].y;
     }
   }
-  for (; s < K.nseg; s++) {
+  for (; s < K.nslab; s++) {
     const float2 v = pp[(size_t)s * seg_stride];
     acc.x += v.x;
     acc.y += v.y;

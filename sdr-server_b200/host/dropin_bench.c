@@ -5,7 +5,12 @@
  * batch binding.  Measures what sdr-server gets by only re-linking against
  * libxlating_b200.so.
  *
- * usage: dropin_bench <clients> <blocks> [window]     (2.016 Msps cu8, 48/96 ksps mixed)
+ * usage: dropin_bench <clients> <blocks> [window [warmup_blocks]]     (2.016 Msps cu8, 48/96 ksps mixed)
+ *
+ * The timed region starts after `warmup_blocks` (default 16) blocks have gone through the same
+ * threads: a server's one-time start-up work -- the first CUDA call of every dsp thread, the
+ * page-locked result ring of the band's batch group (hundreds of MB for hundreds of clients),
+ * filters joining the group -- is not what this measures.
  *
  * window = 0: every dsp thread free-runs through its blocks (pure throughput).
  * window = W > 0: an SDR thread delivers block b to all clients at once, and only after
@@ -27,7 +32,8 @@
 
 #define BLOCK 262144
 
-static int g_window = 0, g_clients = 0, g_blocks = 0;
+static int g_window = 0, g_clients = 0, g_blocks = 0, g_warmup = 16;
+static pthread_barrier_t g_warm_barrier; /* all dsp threads + main: end of warm-up = start of the timed region */
 /* the SDR thread: block p is delivered to every client queue (one semaphore per
  * client, like the reference's one mutex + condition per queue, src/queue.c:87-112) once
  * all clients have finished block p - window */
@@ -63,6 +69,11 @@ static void *dsp_thread(void *arg) {
   xlating_cf32 *out = NULL;
   size_t n = 0;
   for (int b = 0; b < c->n_blocks; b++) {
+    if (b == g_warmup) {
+      pthread_barrier_wait(&g_warm_barrier); /* everybody has finished the warm-up blocks */
+      pthread_barrier_wait(&g_warm_barrier); /* main has taken t0 */
+      c->outputs = 0;
+    }
     if (g_window > 0) wait_for_block(c->id);
     /* every SDR block is new data, and every client holds the same bytes of it */
     memcpy(c->blocks[b % 4] + 64, &b, sizeof(b));
@@ -77,9 +88,12 @@ int main(int argc, char **argv) {
   const int n_clients = argc > 1 ? atoi(argv[1]) : 64;
   const int n_blocks = argc > 2 ? atoi(argv[2]) : 50;
   g_window = argc > 3 ? atoi(argv[3]) : 0;
+  g_warmup = argc > 4 ? atoi(argv[4]) : 16;
+  if (g_warmup < 1) g_warmup = 1;
   g_clients = n_clients;
-  g_blocks = n_blocks;
-  g_finished = (atomic_int *)calloc((size_t)n_blocks, sizeof(atomic_int));
+  g_blocks = n_blocks + g_warmup; /* warm-up blocks first, then the timed ones */
+  pthread_barrier_init(&g_warm_barrier, NULL, (unsigned)n_clients + 1);
+  g_finished = (atomic_int *)calloc((size_t)g_blocks, sizeof(atomic_int));
   g_queue = (sem_t *)calloc((size_t)n_clients, sizeof(sem_t));
   for (int c = 0; c < n_clients; c++) sem_init(&g_queue[c], 0, 0);
   sem_init(&g_sdr, 0, 0);
@@ -111,7 +125,7 @@ int main(int argc, char **argv) {
       clients[c].blocks[i] = (uint8_t *)malloc(BLOCK);
       memcpy(clients[c].blocks[i], master[i], BLOCK);
     }
-    clients[c].n_blocks = n_blocks;
+    clients[c].n_blocks = g_blocks;
     clients[c].id = c;
   }
   /* warm-up: one block each, sequentially */
@@ -122,10 +136,16 @@ int main(int argc, char **argv) {
   }
   pthread_t *threads = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_clients);
   struct timespec t0, t1;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
   pthread_t sdr;
   for (int c = 0; c < n_clients; c++) pthread_create(&threads[c], NULL, dsp_thread, &clients[c]);
   if (g_window > 0) pthread_create(&sdr, NULL, sdr_thread, NULL);
+  pthread_barrier_wait(&g_warm_barrier);
+  uint64_t st0[7] = {0, 0, 0, 0, 0, 0, 0}, ns0[7] = {0, 0, 0, 0, 0, 0, 0}, batches0 = 0, calls0 = 0, shared0 = 0;
+  xlg_dropin_stats(0, &batches0, &calls0, &shared0);
+  xlg_dropin_stream_stats(0, st0);
+  xlg_dropin_stream_times(0, ns0);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_barrier_wait(&g_warm_barrier);
   for (int c = 0; c < n_clients; c++) pthread_join(threads[c], NULL);
   if (g_window > 0) pthread_join(sdr, NULL);
   clock_gettime(CLOCK_MONOTONIC, &t1);
@@ -134,10 +154,15 @@ int main(int argc, char **argv) {
   for (int c = 0; c < n_clients; c++) outputs += clients[c].outputs;
   uint64_t batches = 0, calls = 0, shared = 0;
   xlg_dropin_stats(0, &batches, &calls, &shared); /* stays 0 with XLATING_B200_DROPIN=group */
+  batches -= batches0;
+  calls -= calls0;
+  shared -= shared0;
   uint64_t st[7] = {0, 0, 0, 0, 0, 0, 0};
   xlg_dropin_stream_stats(0, st); /* the band's stream overlay (csrc/stream_overlay.h) */
   uint64_t ns[7] = {0, 0, 0, 0, 0, 0, 0};
   xlg_dropin_stream_times(0, ns);
+  for (int i = 0; i < 6; i++) st[i] -= st0[i]; /* st[6] = members now */
+  for (int i = 0; i < 7; i++) ns[i] -= ns0[i];
   if (st[0] > 0 && st[1] > 0)
     fprintf(stderr, "overlay: per served call %.1f us (compare %.1f, wait for the block %.1f, copy out %.1f); per published "
                     "block: copy %.1f us, submit %.1f us, wait GPU %.1f us\n",
