@@ -96,6 +96,16 @@ class AutoStream {
     int client = -1;       // group client id while a member
     int64_t pos = -1;      // log index of the block this filter consumes next (-1: not tracking)
     int64_t run = 0;       // samples of CONSECUTIVE log blocks consumed, ending at pos-1
+    int lane = -1;         // which of the kLanes futex words this filter sleeps on (assigned at first use)
+  };
+  // Hundreds of dsp threads wait for the same event (a block's results, a publisher's append).  On ONE
+  // futex word every wait and the final wake-all go through one kernel hash bucket and its spinlock --
+  // measured: the serialised cost per caller GROWS with the number of callers (4 us at 256 threads, 10 us
+  // at 1000).  So every event has kLanes words on separate cache lines, a filter always sleeps on the same
+  // lane, and whoever signals the event sets and wakes them all.
+  static constexpr int kLanes = 16;
+  struct alignas(64) Word {
+    std::atomic<int> v{-1};
   };
   struct Served {
     int64_t ticket;
@@ -160,10 +170,11 @@ class AutoStream {
         const uint64_t t0 = now_ns();
         const bool same = mine ? e.seq.load(std::memory_order_acquire) == k : matches(e, k, input, bytes, fmt);
         const uint64_t t1 = now_ns();
-        ns_compare_.fetch_add(t1 - t0, std::memory_order_relaxed);
+        Shard &sh = shards_[(size_t)lane_of(m)];
+        sh.ns_compare.fetch_add(t1 - t0, std::memory_order_relaxed);
         if (!same) break;  // recycled or different bytes: desync
-        const bool ready = wait_done(e, k);
-        ns_wait_.fetch_add(now_ns() - t1, std::memory_order_relaxed);
+        const bool ready = wait_done(e, k, lane_of(m));
+        sh.ns_wait.fetch_add(now_ns() - t1, std::memory_order_relaxed);
         if (!ready) break;
         const int64_t ticket = e.ticket;
         std::atomic_thread_fence(std::memory_order_acquire);
@@ -172,11 +183,11 @@ class AutoStream {
         sv->client = m.client;
         m.pos = k + 1;
         m.run += (int64_t)(elems / 2);
-        hits_.fetch_add(1, std::memory_order_relaxed);
+        sh.hits.fetch_add(1, std::memory_order_relaxed);
         return 1;
       }
       // k == h + 1: nobody has brought this block yet
-      const int rc = publish(k, h, input, bytes, fmt, elems);
+      const int rc = publish(k, h, input, bytes, fmt, elems, false, lane_of(m));
       if (rc < 0) break;  // the log cannot take the block: serve it privately
       mine = rc == 0;
       // rc == 0: published by this caller, rc == 1: by somebody else meanwhile -- either way the
@@ -217,7 +228,7 @@ class AutoStream {
       // not in the log.  May this caller append it?
       const bool in_step = m.pos == h + 1 && m.run > 0;
       if (!in_step && n_members_.load() > 0) break;
-      const int rc = publish(h + 1, h, input, bytes, fmt, elems, /*bootstrap_only=*/!in_step);
+      const int rc = publish(h + 1, h, input, bytes, fmt, elems, /*bootstrap_only=*/!in_step, lane_of(m));
       if (rc == 1) continue;  // raced with another publisher: look again
       if (rc < 0) break;
       m.run = in_step ? m.run + n : n;
@@ -273,8 +284,14 @@ class AutoStream {
   }
 
   Stats stats() const {
-    return Stats{published_.load(), hits_.load(),     desyncs_.load(),    joins_.load(),         private_matches_.load(),
-                 ns_compare_.load(), ns_wait_.load(), ns_pub_copy_.load(), ns_pub_submit_.load(), ns_pub_wait_.load()};
+    uint64_t hits = 0, ns_compare = 0, ns_wait = 0;
+    for (const Shard &sh : shards_) {
+      hits += sh.hits.load();
+      ns_compare += sh.ns_compare.load();
+      ns_wait += sh.ns_wait.load();
+    }
+    return Stats{published_.load(), hits,    desyncs_.load(),     joins_.load(),         private_matches_.load(),
+                 ns_compare,        ns_wait, ns_pub_copy_.load(), ns_pub_submit_.load(), ns_pub_wait_.load()};
   }
 
  private:
@@ -290,7 +307,7 @@ class AutoStream {
     // The index is part of the word because the thread that published block k may be
     // preempted between the GPU finishing and its store: by then the entry may hold
     // block k + R, and a plain "done = 1" would release that block's readers early.
-    std::atomic<int> done{-1};
+    Word done[kLanes];
   };
 
   static void futex_wait(std::atomic<int> *w, int expected) {
@@ -316,28 +333,49 @@ class AutoStream {
   }
 
   static int done_tag(int64_t k) { return (int)((uint32_t)(k & 0x1fffffff) << 2); }
+  int lane_of(Member &m) {
+    if (m.lane < 0) m.lane = (int)(next_lane_.fetch_add(1, std::memory_order_relaxed) % kLanes);
+    return m.lane;
+  }
+  // spin for a few microseconds first: by the time a caller has compared its 256 KiB the block is often
+  // about to be ready, and a futex sleep + wake costs more than that
+  static void wait_word(std::atomic<int> *w, int expected, long timeout_us) {
+    for (int i = 0; i < 400; i++) {
+      if (w->load(std::memory_order_acquire) != expected) return;
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (timeout_us > 0)
+      futex_wait_us(w, expected, timeout_us);
+    else
+      futex_wait(w, expected);
+  }
 
-  bool wait_done(Entry &e, int64_t k) {
+  bool wait_done(Entry &e, int64_t k, int lane) {
     const int tag = done_tag(k);
+    std::atomic<int> *w = &e.done[lane].v;
     for (;;) {
-      const int d = e.done.load(std::memory_order_acquire);
+      const int d = w->load(std::memory_order_acquire);
       if (e.seq.load() != k) return false;  // recycled: this filter lagged a whole ring
       if (d == (tag | 1)) return true;
       if (d == (tag | 2)) return false;
-      if (d == tag) futex_wait(&e.done, tag);
+      if (d == tag) wait_word(w, tag, 0);
     }
   }
 
   // Append block k = h+1 and queue its submission.  0: appended by this caller; 1: head moved
   // (someone else appended); <0: error, nothing appended.
-  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, bool bootstrap_only = false) {
+  int publish(int64_t k, int64_t h, const void *input, size_t bytes, int fmt, size_t elems, bool bootstrap_only = false,
+              int lane = 0) {
     // When an SDR block lands, every dsp thread arrives here within microseconds with the
     // same new block.  One appends it; the others must NOT queue up on the mutex (255 hand-
     // offs of a contended lock, each a futex round trip, cost milliseconds per block): they
     // sleep until the head moves and then take the lock-free reader path.
     std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
     if (!lk.owns_lock()) {
-      if (head_word_.load(std::memory_order_acquire) == (int)h) futex_wait_us(&head_word_, (int)h, 200);
+      std::atomic<int> *w = &head_words_[(size_t)(lane >= 0 ? lane : 0)].v;
+      if (w->load(std::memory_order_acquire) == (int)h) wait_word(w, (int)h, 200);
       return 1;
     }
     if (head_.load() != h) return 1;
@@ -359,16 +397,16 @@ class AutoStream {
     e->fmt = fmt;
     e->elems = elems;
     e->ticket = -1;
-    e->done.store(done_tag(k));
+    for (Word &w : e->done) w.v.store(done_tag(k));
     e->seq.store(k, std::memory_order_release);
     head_.store(k, std::memory_order_release);
-    head_word_.store((int)k, std::memory_order_release);
+    for (Word &w : head_words_) w.v.store((int)k, std::memory_order_release);
     Task t;
     t.kind = Task::kSubmit;
     t.k = k;
     enqueue(t);
     lk.unlock();
-    futex_wake_all(&head_word_);
+    for (Word &w : head_words_) futex_wake_all(&w.v);
     published_.fetch_add(1, std::memory_order_relaxed);
     return 0;
   }
@@ -406,9 +444,11 @@ class AutoStream {
     return rc;
   }
   void finish(Entry &e, int64_t k, bool ok) {
-    int pending = done_tag(k);
-    e.done.compare_exchange_strong(pending, done_tag(k) | (ok ? 1 : 2));  // fails if the entry was recycled
-    futex_wake_all(&e.done);
+    for (Word &w : e.done) {
+      int pending = done_tag(k);
+      w.v.compare_exchange_strong(pending, done_tag(k) | (ok ? 1 : 2));  // fails if the entry was recycled
+    }
+    for (Word &w : e.done) futex_wake_all(&w.v);
   }
   void submitter_main() {
     for (;;) {
@@ -482,10 +522,17 @@ class AutoStream {
   std::deque<Pending> waits_;
   std::thread submitter_, waiter_;
   std::atomic<int64_t> head_{-1};
-  std::atomic<int> head_word_{-1};  // low bits of head_, the futex word followers of a publisher sleep on
+  Word head_words_[kLanes];  // low bits of head_: the futex words followers of a publisher sleep on
+  std::atomic<unsigned> next_lane_{0};
   std::atomic<int> n_members_{0};
-  std::atomic<uint64_t> published_{0}, hits_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
-  std::atomic<uint64_t> ns_compare_{0}, ns_wait_{0}, ns_pub_copy_{0}, ns_pub_submit_{0}, ns_pub_wait_{0};
+  std::atomic<uint64_t> published_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
+  std::atomic<uint64_t> ns_pub_copy_{0}, ns_pub_submit_{0}, ns_pub_wait_{0};
+  // per-call counters are sharded by lane: one shared counter would be one more cache line that every
+  // caller of every block bounces between the sockets
+  struct alignas(64) Shard {
+    std::atomic<uint64_t> hits{0}, ns_compare{0}, ns_wait{0};
+  };
+  Shard shards_[kLanes];
 };
 
 }  // namespace xl

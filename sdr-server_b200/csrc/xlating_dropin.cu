@@ -157,8 +157,11 @@ struct Engine {
   bool overlay = true;       // XLATING_B200_STREAM=0 turns it off
   int stream_ring = 64;      // XLATING_B200_STREAM_RING
   std::vector<StreamHost *> streams;  // guarded by mu
-  std::atomic<uint64_t> stream_served{0};
-  std::atomic<uint64_t> stream_copy_ns{0}, stream_call_ns{0};  // time in xlg_copy_output / in whole served calls
+  // served calls, time in xlg_copy_output / in whole served calls -- sharded like the overlay's counters
+  struct alignas(64) ServedShard {
+    std::atomic<uint64_t> served{0}, copy_ns{0}, call_ns{0};
+  };
+  ServedShard served[AutoStream::kLanes];
 };
 constexpr size_t kPoolMaxBytes = (size_t)2 << 30;  // device + pinned bytes kept for reuse
 
@@ -740,7 +743,8 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
       xlg_client_state st;
       const uint64_t t_copy = AutoStream::now_ns();
       const int rc = xlg_copy_output(f->sh->g, sv.ticket, sv.client, f->h_out, (size_t)f->out_cap, &got, &st);
-      e->stream_copy_ns.fetch_add(AutoStream::now_ns() - t_copy, std::memory_order_relaxed);
+      Engine::ServedShard &shard = e->served[(size_t)(f->as_m.lane >= 0 ? f->as_m.lane : 0)];
+      shard.copy_ns.fetch_add(AutoStream::now_ns() - t_copy, std::memory_order_relaxed);
       if (rc == 0 && got == want) {
         f->hist = st.hist;
         f->ph_re = st.phase_re;
@@ -748,8 +752,8 @@ void run_block(xlating *f, int fmt, const void *input, size_t input_len, bool q1
         tail_push(f, fmt, input, (size_t)n);
         f->S += n;
         f->dev_stale = true;
-        e->stream_served.fetch_add(1, std::memory_order_relaxed);
-        e->stream_call_ns.fetch_add(AutoStream::now_ns() - t_call, std::memory_order_relaxed);
+        shard.served.fetch_add(1, std::memory_order_relaxed);
+        shard.call_ns.fetch_add(AutoStream::now_ns() - t_call, std::memory_order_relaxed);
         *output_len = got;
         return;
       }
@@ -884,8 +888,10 @@ int xlg_dropin_stream_times(int device, uint64_t *ns7) {
   if (it == g_engines.end() || ns7 == NULL) return -ENOENT;
   Engine *e = it->second;
   memset(ns7, 0, 7 * sizeof(uint64_t));
-  ns7[0] = e->stream_call_ns.load();
-  ns7[1] = e->stream_copy_ns.load();
+  for (const Engine::ServedShard &sh : e->served) {
+    ns7[0] += sh.call_ns.load();
+    ns7[1] += sh.copy_ns.load();
+  }
   std::lock_guard<std::mutex> lk2(e->mu);
   for (StreamHost *sh : e->streams) {
     AutoStream *as = sh->as.load();
@@ -906,7 +912,7 @@ int xlg_dropin_stream_stats(int device, uint64_t *stats7) {
   if (it == g_engines.end() || stats7 == NULL) return -ENOENT;
   Engine *e = it->second;
   memset(stats7, 0, 7 * sizeof(uint64_t));
-  stats7[0] = e->stream_served.load();
+  for (const Engine::ServedShard &sh : e->served) stats7[0] += sh.served.load();
   std::lock_guard<std::mutex> lk2(e->mu);
   for (StreamHost *sh : e->streams) {
     AutoStream *as = sh->as.load();

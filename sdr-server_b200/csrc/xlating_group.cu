@@ -237,7 +237,7 @@ struct xlg_group {
   void *d_tile_taps = nullptr;
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
   int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long3 / fir_long2) or 64 (XLATING_B200_LONG=1)
-  int long_gen = 3;       // XLATING_B200_LONG=1|2|3: which long-filter kernel (3 = pipelined, the default)
+  int long_gen = 4;       // XLATING_B200_LONG=1|2|3|4: which long-filter kernel (4 = pipelined 28 x 64 tile, the default)
   int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
   int *d_member_cid = nullptr;      // client id per member slot (-1 = padding)
@@ -960,7 +960,7 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     const char *tv = getenv("XLATING_B200_TILE");
     if (tv != nullptr) g->tile_force = atoi(tv);
     const char *lv = getenv("XLATING_B200_LONG");
-    if (lv != nullptr && atoi(lv) >= 1 && atoi(lv) <= 3) g->long_gen = atoi(lv);  // A/B of the long-filter kernels
+    if (lv != nullptr && atoi(lv) >= 1 && atoi(lv) <= 4) g->long_gen = atoi(lv);  // A/B of the long-filter kernels
     if (g->long_gen == 1) g->long_kt = W_KT;
     const char *sv = getenv("XLATING_B200_SPECULATE");
     if (sv != nullptr) g->speculate = atoi(sv) != 0;
@@ -978,7 +978,8 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
           cudaSuccess ||
       cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fir_long2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(fir_long3_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(fir_long3_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fir_long4_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
@@ -1443,7 +1444,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     int ctas = 0, max_out = 0, max_groups = 0;
     // the pipelined kernel needs 16-byte aligned strips (even decimation and window start) for its TMA
     // bulk copies; fir_long2 takes over otherwise (it can fall back to 8-byte cp.async)
-    bool pipelined = g->long_gen == 3;
+    bool pipelined = g->long_gen >= 3;
+    const bool wide = g->long_gen == 4;  // 28 outputs x 2 groups per CTA instead of 56 x 1
     for (TileClassHost &ch : g->long_classes) {
       const HostClient &h0 = g->clients[ch.real[0]];
       const int n_out = ho.n_out[ch.real[0]];
@@ -1467,12 +1469,15 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       k.seg_per = 1;
       if (pipelined) {
         // one resident CTA per SM: as many CTAs along the tap axis as fill one wave of this class's share
+        const int units = wide ? ((n_out + W4_KT - 1) / W4_KT) * ((k.n_groups + W4_GROUPS - 1) / W4_GROUPS)
+                               : k.tiles * k.n_groups;
+        if (wide) k.tiles = (n_out + W4_KT - 1) / W4_KT;  // (kpad, a multiple of 56, covers 2 x 28 too)
         const int share = std::max(1, g->fir_sms / std::max(n_live, 1));
-        const int want = std::max(1, share / std::max(1, k.tiles * k.n_groups));
+        const int want = std::max(1, share / std::max(1, units));
         k.seg_per = (k.nseg + std::min(want, k.nseg) - 1) / std::min(want, k.nseg);
         k.ksplit = (k.nseg + k.seg_per - 1) / k.seg_per;
         k.nslab = k.ksplit;
-        ctas += k.ksplit * k.tiles * k.n_groups;
+        ctas += k.ksplit * units;
       } else {
         ctas += k.nseg * k.tiles * k.n_groups;
       }
@@ -1486,7 +1491,10 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
         CU_OK(cudaEventRecord(s.pf[8], cs));
         s.pf_long = true;
       }
-      if (pipelined)
+      if (pipelined && wide)
+        fir_long4_cf32_kernel<<<ctas, W3_THREADS, W4_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
+                                                                s.d_partial);
+      else if (pipelined)
         fir_long3_cf32_kernel<<<ctas, W3_THREADS, W3_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
                                                                 s.d_partial);
       else if (g->long_kt == W2_KT)

@@ -1064,6 +1064,172 @@ fir_long3_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// fir_long4: the pipelined kernel with a 28-output x 64-client tile (4 output lanes x 7 outputs
+// per thread, 8 client octets = TWO 32-client groups per CTA).  Same FLOPs per stage as fir_long3's
+// 56 x 32, but a stage is 28 strips + 2 tap blocks = 30 bulk copies instead of 57.  The three
+// earlier kernels all run at ~300 cycles per 1 KiB strip copy and SM whatever else they do
+// (745 copies per SM and block in 113-121 us): small bulk copies, not FMAs, are what they wait for.
+// ---------------------------------------------------------------------------
+constexpr int W4_LO = 4;
+constexpr int W4_KT = W4_LO * W2_RK;    // 28 outputs per CTA
+constexpr int W4_GROUPS = 2;            // client groups per CTA
+constexpr int W4_STAGE_BYTES = W4_GROUPS * W_JS * T_CG * 8 + W4_KT * W_JSP * 8;  // 64 KiB taps + 28.4 KiB strips
+constexpr int W4_SMEM = W3_STAGES * W4_STAGE_BYTES + 64;
+static_assert((W3_WARPS - 1) * 32 * W2_RK * T_RC * 2 * 4 <= W3_STAGES * W4_STAGE_BYTES, "reduction scratch reuses the stages");
+
+__global__ void __launch_bounds__(W3_THREADS, 1)
+fir_long4_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
+                      const float2 *__restrict__ tile_taps, float2 *__restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W3_STAGES * W4_STAGE_BYTES);  // full[2], empty[2]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o = lane & (W4_LO - 1), h = lane / W4_LO;  // output column, client octet (0..7)
+  const int gsel = h >> 2;                              // which of the CTA's two groups
+  const int cbase = (h & 3) * T_RC;
+
+  const int ci = class_of_cta(P, (int)blockIdx.x);
+  const TileClass &K = P.cls[ci];
+  const int local = (int)blockIdx.x - K.cta_begin;
+  const int sp = local % K.ksplit;
+  const int rest = local / K.ksplit;
+  const int tile = rest % K.tiles;
+  const int gpair = rest / K.tiles;
+  const int k0 = tile * W4_KT;
+  const int D = K.D;
+  const int seg_begin = sp * K.seg_per;
+  const int seg_end = min(seg_begin + K.seg_per, K.nseg);
+  const int grp0 = gpair * W4_GROUPS;
+  const int n_grp = min(W4_GROUPS, K.n_groups - grp0);           // 1 or 2 real groups in this CTA
+  const bool mine_active = gsel < n_grp && (grp0 + gsel) * T_CG < K.n_members;
+
+  if (tid == 0) {
+    for (int st = 0; st < W3_STAGES; st++) {
+      mbar_init(&bars[st], 1);
+      mbar_init(&bars[W3_STAGES + st], W3_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto load_segment = [&](int sg, int st) {
+    const int f0 = sg * W_JS;
+    const int len = min(W_JS, K.L - f0);
+    float2 *ts = reinterpret_cast<float2 *>(smem + st * W4_STAGE_BYTES);
+    float2 *xs = ts + W4_GROUPS * W_JS * T_CG;
+    const unsigned strip_bytes = (unsigned)len * 8u, tap_bytes = (unsigned)len * T_CG * 8u;
+    if (lane == 0) mbar_expect_tx(&bars[st], (unsigned)n_grp * tap_bytes + W4_KT * strip_bytes);
+    __syncwarp();
+    if (lane < n_grp)
+      tma_bulk_g2s(ts + lane * W_JS * T_CG, tile_taps + K.taps_off + ((long long)(grp0 + lane) * K.L + f0) * T_CG, tap_bytes,
+                   &bars[st]);
+    const long long w0 = K.first + (long long)k0 * D + f0;
+    if (lane < W4_KT) {
+      const unsigned idx = (unsigned)((unsigned long long)(w0 + (long long)lane * D)) & mask;
+      const unsigned n1 = min((unsigned)len, mask + 1u - idx);
+      tma_bulk_g2s(xs + lane * W_JSP, ring + idx, n1 * 8u, &bars[st]);
+      if (n1 < (unsigned)len) tma_bulk_g2s(xs + lane * W_JSP + n1, ring, ((unsigned)len - n1) * 8u, &bars[st]);
+    }
+  };
+
+  float2 acc[W2_RK][T_RC];
+#pragma unroll
+  for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+    for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+
+  if (seg_begin < seg_end) {
+    if (warp == 0) load_segment(seg_begin, 0);
+    for (int sg = seg_begin; sg < seg_end; sg++) {
+      const int it = sg - seg_begin, st = it % W3_STAGES;
+      if (warp == 0 && sg + 1 < seg_end) {
+        const int ns = (it + 1) % W3_STAGES;
+        if (it >= 1) mbar_wait(&bars[W3_STAGES + ns], (unsigned)(((it - 1) / W3_STAGES) & 1));
+        load_segment(sg + 1, ns);
+      }
+      mbar_wait(&bars[st], (unsigned)((it / W3_STAGES) & 1));
+      if (mine_active) {
+        const int len = min(W_JS, K.L - sg * W_JS);
+        const float2 *ts = reinterpret_cast<const float2 *>(smem + st * W4_STAGE_BYTES);
+        const float2 *xs = ts + W4_GROUPS * W_JS * T_CG;
+        const float4 *tp = reinterpret_cast<const float4 *>(ts + gsel * W_JS * T_CG + cbase);
+        const float2 *xb[W2_RK];
+#pragma unroll
+        for (int i = 0; i < W2_RK; i++) xb[i] = xs + (o + W4_LO * i) * W_JSP;
+        const int f_end = min(len, (warp + 1) * W3_JW);
+#pragma unroll 1
+        for (int f = warp * W3_JW; f < f_end; f += T_UNROLL) {
+#pragma unroll
+          for (int u = 0; u < T_UNROLL; u++) {
+            float2 x[W2_RK];
+            float4 tq[T_RC / 2];
+#pragma unroll
+            for (int i = 0; i < W2_RK; i++) x[i] = xb[i][f + u];
+#pragma unroll
+            for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+            for (int i = 0; i < W2_RK; i++) {
+#pragma unroll
+              for (int q = 0; q < T_RC / 2; q++) {
+                float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+                a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+                a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+                a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+                a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+                a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+                a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+                a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+                a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[W3_STAGES + st]);  // this warp is done with the stage
+    }
+  }
+  // warps 1..7 hand their sums to warp 0 through shared memory, layout [warp-1][value][lane]
+  __syncthreads();
+  float *red = reinterpret_cast<float *>(smem);
+  constexpr int NV = W2_RK * T_RC * 2;
+  if (warp > 0) {
+    float *dst = red + (size_t)(warp - 1) * NV * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+      for (int c = 0; c < T_RC; c++) {
+        dst[(size_t)((i * T_RC + c) * 2) * 32] = acc[i][c].x;
+        dst[(size_t)((i * T_RC + c) * 2 + 1) * 32] = acc[i][c].y;
+      }
+  }
+  __syncthreads();
+  if (warp == 0 && mine_active) {
+#pragma unroll 1
+    for (int w = 0; w < W3_WARPS - 1; w++) {
+      const float *src = red + (size_t)w * NV * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+        for (int c = 0; c < T_RC; c++) {
+          acc[i][c].x += src[(size_t)((i * T_RC + c) * 2) * 32];
+          acc[i][c].y += src[(size_t)((i * T_RC + c) * 2 + 1) * 32];
+        }
+    }
+    // partial sums: [tap split][group][output][32 clients]
+    float2 *pp = partial + K.part_off + (((long long)sp * K.n_groups + grp0 + gsel) * K.kpad + k0) * T_CG + cbase;
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++) {
+      float4 *row = reinterpret_cast<float4 *>(pp + (size_t)(o + W4_LO * i) * T_CG);
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++)
+        row[q] = make_float4(acc[i][2 * q].x, acc[i][2 * q].y, acc[i][2 * q + 1].x, acc[i][2 * q + 1].y);
+    }
+  }
+}
+
 // Adds the segments in order, derotates, stores.  Block = 32 clients (lanes) x 8 outputs.
 __global__ void __launch_bounds__(256)
 fir_long_reduce_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ partial,
