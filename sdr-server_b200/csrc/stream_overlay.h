@@ -317,6 +317,9 @@ class AutoStream {
     struct timespec ts = {us / 1000000, (us % 1000000) * 1000};
     syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAIT_PRIVATE, expected, &ts, nullptr, 0);
   }
+  static void futex_wake_n(std::atomic<int> *w, int n) {
+    syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAKE_PRIVATE, n, nullptr, nullptr, 0);
+  }
   static void futex_wake_all(std::atomic<int> *w) {
     syscall(SYS_futex, reinterpret_cast<int *>(w), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
   }
@@ -339,8 +342,11 @@ class AutoStream {
   }
   // spin for a few microseconds first: by the time a caller has compared its 256 KiB the block is often
   // about to be ready, and a futex sleep + wake costs more than that
+  // Waking a sleeper costs the WAKER 2-5 us of kernel time, so one thread waking a thousand takes
+  // milliseconds (measured).  The signaller therefore wakes ONE sleeper per lane, and every sleeper that
+  // wakes up wakes two more of its lane before it goes on: the wake-up fans out as a tree, on many CPUs.
   static void wait_word(std::atomic<int> *w, int expected, long timeout_us) {
-    for (int i = 0; i < 400; i++) {
+    for (int i = 0; i < 40; i++) {  // a few microseconds: the event is often about to happen
       if (w->load(std::memory_order_acquire) != expected) return;
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
@@ -350,6 +356,7 @@ class AutoStream {
       futex_wait_us(w, expected, timeout_us);
     else
       futex_wait(w, expected);
+    if (w->load(std::memory_order_acquire) != expected) futex_wake_n(w, 2);
   }
 
   bool wait_done(Entry &e, int64_t k, int lane) {
@@ -406,7 +413,7 @@ class AutoStream {
     t.k = k;
     enqueue(t);
     lk.unlock();
-    for (Word &w : head_words_) futex_wake_all(&w.v);
+    for (Word &w : head_words_) futex_wake_n(&w.v, 1);
     published_.fetch_add(1, std::memory_order_relaxed);
     return 0;
   }
@@ -448,7 +455,7 @@ class AutoStream {
       int pending = done_tag(k);
       w.v.compare_exchange_strong(pending, done_tag(k) | (ok ? 1 : 2));  // fails if the entry was recycled
     }
-    for (Word &w : e.done) futex_wake_all(&w.v);
+    for (Word &w : e.done) futex_wake_n(&w.v, 1);
   }
   void submitter_main() {
     for (;;) {

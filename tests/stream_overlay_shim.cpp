@@ -264,7 +264,7 @@ int main(int argc, char **argv) {
       if (b % window == 0) pthread_barrier_wait(&bar);
       if (b < start) continue;
       if (drops && i % 3 == 0 && b > 5 && r() % 11 == 0) continue;  // the client's queue dropped this block
-      if (lag && i == 3 && b == 20) usleep(30000);                  // one client stalls for a long time
+      if (lag && i == 3 && b == 20) usleep(400000);                 // one client stalls for a long time
       if (r() % 4 == 0) usleep((useconds_t)(r() % 200));
       const std::vector<uint8_t> &blk = src[(size_t)s][(size_t)b];
       std::vector<uint8_t> own(blk);  // private copy, like queue_put's memcpy (src/queue.c:114)
