@@ -343,8 +343,9 @@ class AutoStream {
   // spin for a few microseconds first: by the time a caller has compared its 256 KiB the block is often
   // about to be ready, and a futex sleep + wake costs more than that
   // Waking a sleeper costs the WAKER 2-5 us of kernel time, so one thread waking a thousand takes
-  // milliseconds (measured).  The signaller therefore wakes ONE sleeper per lane, and every sleeper that
-  // wakes up wakes two more of its lane before it goes on: the wake-up fans out as a tree, on many CPUs.
+  // milliseconds (measured).  The signaller therefore wakes ONE sleeper per lane, and that one wakes the
+  // rest of its lane before it goes on: two levels, the second spread over kLanes CPUs.  (A binary tree --
+  // every sleeper wakes two more -- was measured too: its depth costs more than it saves at 256 threads.)
   static void wait_word(std::atomic<int> *w, int expected, long timeout_us) {
     for (int i = 0; i < 40; i++) {  // a few microseconds: the event is often about to happen
       if (w->load(std::memory_order_acquire) != expected) return;
@@ -356,7 +357,7 @@ class AutoStream {
       futex_wait_us(w, expected, timeout_us);
     else
       futex_wait(w, expected);
-    if (w->load(std::memory_order_acquire) != expected) futex_wake_n(w, 2);
+    if (w->load(std::memory_order_acquire) != expected) futex_wake_all(w);  // the first one up wakes the rest of its lane
   }
 
   bool wait_done(Entry &e, int64_t k, int lane) {
