@@ -95,6 +95,12 @@ typedef struct {
 int xlg_add_client_ex(xlg_group *g, uint32_t decimation, const float *taps, size_t taps_len, int32_t center_freq,
                       const xlg_client_state *state, int *client_id);
 int xlg_remove_client(xlg_group *g, int client_id);
+/* Size the per-ticket result arenas (device and pinned host) for `output_samples_per_block` complex output
+ * samples per block summed over all clients (a client at decimation D produces about max_input_len/2/D + 2).
+ * Optional: the arenas grow on demand when clients are added, but a growth re-allocates every ring entry and
+ * the results still waiting in the ring are lost (-ESTALE for consumers that had not read them yet, like a
+ * block overwritten in the reference's queue).  A server that knows its client limit reserves once, up front. */
+int xlg_reserve(xlg_group *g, size_t output_samples_per_block);
 int xlg_client_count(const xlg_group *g);
 
 /* Submit one block for ALL clients.  `input_len` in scalar elements.  Returns a

@@ -48,7 +48,7 @@ REFERENCE_SYMBOLS = (
     + [f"process_{v}_{f}_{o}" for v in ("native", "optimized") for f in ("cu8", "cs8", "cs16") for o in ("cf32", "cs16")]
 )
 GROUP_SYMBOLS = [
-    "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_add_client_ex", "xlg_remove_client", "xlg_client_count", "xlg_submit",
+    "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_add_client_ex", "xlg_remove_client", "xlg_reserve", "xlg_client_count", "xlg_submit",
     "xlg_wait", "xlg_input_consumed", "xlg_output", "xlg_read_output", "xlg_copy_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
     "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats", "xlg_dropin_stream_stats", "xlg_dropin_stream_times",
 ]
@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
     L.xlg_destroy.restype = None
     L.xlg_add_client.argtypes = [vp, u32, C.POINTER(C.c_float), sz, i32, C.POINTER(C.c_int)]
     L.xlg_add_client.restype = C.c_int
+    L.xlg_reserve.argtypes = [vp, sz]
+    L.xlg_reserve.restype = C.c_int
     L.xlg_remove_client.argtypes = [vp, C.c_int]
     L.xlg_remove_client.restype = C.c_int
     L.xlg_client_count.argtypes = [vp]
@@ -267,6 +269,11 @@ class Group:
         code = self._L.xlg_remove_client(self._h, cid)
         if code != 0:
             raise ValueError(code)
+
+    def reserve(self, output_samples_per_block: int) -> None:
+        code = self._L.xlg_reserve(self._h, output_samples_per_block)
+        if code != 0:
+            raise RuntimeError(f"xlg_reserve -> {code}")
 
     def client_count(self) -> int:
         return self._L.xlg_client_count(self._h)

@@ -1131,6 +1131,15 @@ extern "C" int xlg_add_client_ex(xlg_group *g, uint32_t decimation, const float 
   return 0;
 }
 
+extern "C" int xlg_reserve(xlg_group *g, size_t output_samples_per_block) {
+  if (g == nullptr) return -EINVAL;
+  CU_OK(cudaSetDevice(g->device));
+  if (output_samples_per_block <= g->arena_cap) return 0;
+  if (drain(g)) return -EIO;
+  // ensure_arenas adds 25 % on top: ask for exactly what was requested
+  return ensure_arenas(g, output_samples_per_block - output_samples_per_block / 5, g->q_alloc);
+}
+
 extern "C" int xlg_remove_client(xlg_group *g, int client_id) {
   if (g == nullptr || client_id < 0 || client_id >= (int)g->clients.size() || !g->clients[client_id].active)
     return -EINVAL;

@@ -697,3 +697,34 @@ def test_group_speculative_prepass_hits_and_rollbacks(pkg):
             for cid, o in zip(ids, oracles):
                 assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"step {step} client {cid}")
     g.close()
+
+
+def test_group_reserve_keeps_unread_results_when_clients_are_added(pkg):
+    """growing the result arenas used to invalidate every ticket still waiting in the
+    ring.  With xlg_reserve sized for the final client count, results submitted before 60 more
+    clients attach stay readable (the reference never drops data for the others when a client
+    joins, src/tcp_server.c:301-384)."""
+    rng = np.random.default_rng(97)
+    fs, max_in = 2016000, 32768
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 16400)
+    plan = pkg.client_plan(fs, [48000] * 72, tw=16400)
+    g = pkg.Group(fs, max_in, host_ring=8)
+    g.reserve(72 * (max_in // 2 // 42 + 6))
+    ids = [g.add_client(p["decimation"], taps, p["center"]) for p in plan[:12]]
+    oracles = [po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in) for p in plan[:12]]
+    early = []
+    for _ in range(3):
+        x = rand_block(rng, "cu8", max_in)
+        early.append((g.submit("cu8", x), [o.process_cf32("cu8", x) for o in oracles]))
+    late_ids = [g.add_client(p["decimation"], taps, p["center"]) for p in plan[12:]]
+    late_or = [po.OracleFilter(p["decimation"], taps, p["center"], fs, max_in) for p in plan[12:]]
+    x = rand_block(rng, "cu8", max_in)
+    t = g.submit("cu8", x)  # layout rebuilt for 72 clients; the arenas do not grow
+    g.wait(t)
+    for cid, o in zip(ids + late_ids, oracles + late_or):
+        assert_cf32_close(g.output(t, cid), o.process_cf32("cu8", x), f"client {cid}")
+    for t0, refs in early:  # still there
+        g.wait(t0)
+        for cid, r in zip(ids, refs):
+            assert_cf32_close(g.output(t0, cid), r, f"early ticket {t0} client {cid}")
+    g.close()
