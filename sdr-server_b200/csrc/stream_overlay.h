@@ -129,7 +129,8 @@ class AutoStream {
 
   AutoStream(const StreamOps &ops, int ring, size_t max_block_bytes)
       : ops_(ops), ring_(ring < 4 ? 4 : ring), max_bytes_(max_block_bytes), log_((size_t)(ring < 4 ? 4 : ring)) {
-    if (getenv("XLATING_B200_SPIN_US") != nullptr) spin_us_ = std::min(std::max(atol(getenv("XLATING_B200_SPIN_US")), 0l), 100000l);
+    if (getenv("XLATING_B200_SPIN_ITERS") != nullptr)
+      spin_iters_ = std::min(std::max(atol(getenv("XLATING_B200_SPIN_ITERS")), 0l), 1000000l);
     // the log's block copies are allocated here, by the creating thread, not lazily by whichever
     // dsp thread publishes first (page-locking memory from a fresh thread costs milliseconds)
     for (Entry &e : log_) e.host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
@@ -347,27 +348,19 @@ class AutoStream {
   // spin for a few microseconds first: by the time a caller has compared its 256 KiB the block is often
   // about to be ready, and a futex sleep + wake costs more than that
   // Waiting for an event that is a few hundred microseconds away (a block's results; a publisher's
-  // append).  Sleeping on the futex straight away is the expensive choice when blocks come back to
-  // back: every sleeper costs its waker 2-5 us of kernel time, so waking the callers of one block
-  // takes ~1 ms with 256 dsp threads -- four times what the GPU needs for the block (measured; a
-  // tree of wake-ups, each sleeper waking two or all of its lane, was worse still: every hop is a
-  // scheduling latency).  So a caller first POLLS, yielding its CPU to the other dsp threads between
-  // looks (sched_yield: with more threads than CPUs they take turns), and only sleeps once the event
-  // is late (spin_us_, 400 us by default; XLATING_B200_SPIN_US): a real-time stream, whose blocks
-  // are 65 ms apart, sleeps as before.
+  // append): poll for ~20 us -- by the time a caller has compared its 256 KiB the event is often about
+  // to happen, and a futex sleep costs the sleeper a context switch and its waker 2-5 us of kernel time
+  // -- then sleep.  Measured alternatives, all worse on a 128-thread host (256 dsp threads, MS/s in):
+  // sleeping at once 100-110; a wake-up tree (every sleeper wakes two more) 84; two levels (one sleeper
+  // per lane wakes its lane) 101-113; polling with sched_yield for 400 us 36; this, with the signaller
+  // waking all sixteen lanes itself, 272.  XLATING_B200_SPIN_ITERS changes the polling length.
   void wait_word(std::atomic<int> *w, int expected, long timeout_us) {
-    for (int i = 0; i < 40; i++) {
+    for (long i = 0; i < spin_iters_; i++) {
       if (w->load(std::memory_order_acquire) != expected) return;
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
 #endif
     }
-    const uint64_t t0 = now_ns(), budget = (uint64_t)spin_us_ * 1000ull;
-    while (now_ns() - t0 < budget) {
-      if (w->load(std::memory_order_acquire) != expected) return;
-      sched_yield();
-    }
-    if (w->load(std::memory_order_acquire) != expected) return;
     if (timeout_us > 0)
       futex_wait_us(w, expected, timeout_us);
     else
@@ -470,7 +463,7 @@ class AutoStream {
       int pending = done_tag(k);
       w.v.compare_exchange_strong(pending, done_tag(k) | (ok ? 1 : 2));  // fails if the entry was recycled
     }
-    for (Word &w : e.done) futex_wake_all(&w.v);  // (few sleep: see wait_word)
+    for (Word &w : e.done) futex_wake_all(&w.v);
   }
   void submitter_main() {
     for (;;) {
@@ -546,7 +539,7 @@ class AutoStream {
   std::atomic<int64_t> head_{-1};
   Word head_words_[kLanes];  // low bits of head_: the futex words followers of a publisher sleep on
   std::atomic<unsigned> next_lane_{0};
-  long spin_us_ = 400;  // how long a caller polls (yielding) for an event before it sleeps
+  long spin_iters_ = 400;  // PAUSE iterations (~20 us) a caller polls for an event before it sleeps
   std::atomic<int> n_members_{0};
   std::atomic<uint64_t> published_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
   std::atomic<uint64_t> ns_pub_copy_{0}, ns_pub_submit_{0}, ns_pub_wait_{0};
