@@ -131,6 +131,7 @@ class AutoStream {
       : ops_(ops), ring_(ring < 4 ? 4 : ring), max_bytes_(max_block_bytes), log_((size_t)(ring < 4 ? 4 : ring)) {
     if (getenv("XLATING_B200_SPIN_ITERS") != nullptr)
       spin_iters_ = std::min(std::max(atol(getenv("XLATING_B200_SPIN_ITERS")), 0l), 1000000l);
+    two_level_ = getenv("XLATING_B200_WAKE") != nullptr && strcmp(getenv("XLATING_B200_WAKE"), "two_level") == 0;
     // the log's block copies are allocated here, by the creating thread, not lazily by whichever
     // dsp thread publishes first (page-locking memory from a fresh thread costs milliseconds)
     for (Entry &e : log_) e.host = ops_.alloc_block(ops_.ctx, max_bytes_ > 0 ? max_bytes_ : 1);
@@ -365,6 +366,7 @@ class AutoStream {
       futex_wait_us(w, expected, timeout_us);
     else
       futex_wait(w, expected);
+    if (two_level_ && w->load(std::memory_order_acquire) != expected) futex_wake_all(w);
   }
 
   bool wait_done(Entry &e, int64_t k, int lane) {
@@ -463,7 +465,12 @@ class AutoStream {
       int pending = done_tag(k);
       w.v.compare_exchange_strong(pending, done_tag(k) | (ok ? 1 : 2));  // fails if the entry was recycled
     }
-    for (Word &w : e.done) futex_wake_all(&w.v);
+    for (Word &w : e.done) {
+      if (two_level_)
+        futex_wake_n(&w.v, 1);  // that sleeper wakes the rest of its lane (wait_word)
+      else
+        futex_wake_all(&w.v);
+    }
   }
   void submitter_main() {
     for (;;) {
@@ -539,6 +546,7 @@ class AutoStream {
   std::atomic<int64_t> head_{-1};
   Word head_words_[kLanes];  // low bits of head_: the futex words followers of a publisher sleep on
   std::atomic<unsigned> next_lane_{0};
+  bool two_level_ = false;  // XLATING_B200_WAKE=two_level (measurement switch)
   long spin_iters_ = 400;  // PAUSE iterations (~20 us) a caller polls for an event before it sleeps
   std::atomic<int> n_members_{0};
   std::atomic<uint64_t> published_{0}, desyncs_{0}, joins_{0}, private_matches_{0};
