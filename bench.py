@@ -862,9 +862,9 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     algo_bytes = BLOCK_BYTES + 8 * main_leg["n_out_total"]  # read the block once, write cf32 per client
     dom = max(("fir_tile", "fir_long", "fir_generic"), key=lambda k: prof[f"{k}_ms"])
-    kname = {"fir_tile": "fir_tile_cf32_kernel", "fir_long": "fir_long_cf32_kernel + fir_long_reduce_kernel",
+    kname = {"fir_tile": "fir_tile_cf32_kernel", "fir_long": "fir_long4_cf32_kernel (XLATING_B200_LONG picks 1-4) + fir_long_reduce_kernel",
              "fir_generic": "fir_generic_cf32_kernel"}[dom]
-    kregex = {"fir_tile": "fir_tile_cf32_kernel", "fir_long": "fir_long_cf32_kernel",
+    kregex = {"fir_tile": "fir_tile_cf32_kernel", "fir_long": "fir_long[0-9]?_cf32_kernel",
               "fir_generic": "fir_generic_cf32_kernel"}[dom]
     roof = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
             "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_launch": algo_bytes,
