@@ -63,7 +63,9 @@ enum { XLG_FMT_CU8 = 0, XLG_FMT_CS8 = 1, XLG_FMT_CS16 = 2 };
 /* depth of the device pipeline (blocks in flight).  Outputs of ticket t stay valid
  * until ticket t + XLG_SLOTS (or t + host_ring, see xlg_create_ex) is submitted;
  * after that xlg_wait / xlg_output return -ESTALE. */
+#ifndef XLG_SLOTS
 #define XLG_SLOTS 4
+#endif
 
 /* One wideband stream on CUDA device `device`.  max_input_len is the largest
  * block, in scalar elements (like create_frequency_xlating_filter's

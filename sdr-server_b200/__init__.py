@@ -27,7 +27,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libxlating_b200.so")
+# XLATING_B200_LIB: an A/B measurement switch (another build of the SAME library, e.g. other tile constants)
+LIB_PATH = os.environ.get("XLATING_B200_LIB") or os.path.join(HERE, "lib", "libxlating_b200.so")
 
 FMT = {"cu8": 0, "cs8": 1, "cs16": 2}
 NP_DTYPE = {"cu8": np.uint8, "cs8": np.int8, "cs16": np.int16}

@@ -37,6 +37,8 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <array>
+#include <cstdint>
 #include <vector>
 
 #include "taps_host.h"
@@ -94,6 +96,7 @@ struct Slot {
   size_t blk_cap = 0;
   cudaEvent_t ev_h2d = nullptr, ev_conv = nullptr, ev_phase = nullptr, ev_fir = nullptr, ev_done = nullptr;
   cudaEvent_t pf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tl_ph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // timeline: pre-pass stamps, by occupancy parity (it runs a block ahead)
   bool pf_conv = false, pf_phase = false, pf_tile = false, pf_gen = false, pf_long = false;
   std::atomic<int64_t> ticket{-1};
   bool q15 = false;
@@ -205,6 +208,10 @@ struct xlg_group {
   uint32_t max_input_len = 0;  // scalar elements
   uint32_t flags = 0;
   cudaStream_t s_in = nullptr, s_ph = nullptr, s_out = nullptr;
+  // raw -> ring conversion: its own stream, in the oscillator partition (or at high priority without one), so
+  // that block b+1's conversion never queues behind the CTAs of block b's FIR that are still waiting for an SM
+  cudaStream_t s_cv = nullptr;
+  bool conv_own_stream = true;  // XLATING_B200_CONV_STREAM=0: convert on the block's compute stream (the old order)
   static constexpr int kMaxCs = 4;
   cudaStream_t s_cs[kMaxCs] = {nullptr, nullptr, nullptr, nullptr};  // compute streams, round-robin by block
   int n_cs = 3;  // 3 measured 2.4 % faster than 2 on cfg2 (2129 vs 2079 MS/s), 4 no better
@@ -237,6 +244,8 @@ struct xlg_group {
   void *d_tile_taps = nullptr;
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
   int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long3 / fir_long2) or 64 (XLATING_B200_LONG=1)
+  bool packed = false;    // XLATING_B200_FFMA2=1: tiled kernel on packed FFMA2 (bit-identical; measured 4-8 % slower in
+                          // steady state); decides the tap packing too
   int long_gen = 4;       // XLATING_B200_LONG=1|2|3|4: which long-filter kernel (4 = pipelined 28 x 64 tile, the default)
   int fir_sms = 0;        // SMs the FIR kernels can use (all, or all minus the reserved partition)
   int *d_members = nullptr;
@@ -262,6 +271,14 @@ struct xlg_group {
   std::vector<long long *> retired_meta_ll;
   long long *d_trace = nullptr;  // XLATING_B200_TRACE=1: per-CTA timeline of the tiled kernel
   int trace_ctas = 0;
+  // XLATING_B200_TIMELINE=path: GPU timestamps (ms since the first submit) of every block's kernels in the
+  // REAL pipeline (all streams, speculation on): conv ready/done, phase start/done, FIR ready/done
+  bool timeline = false;
+  cudaEvent_t ev_base = nullptr;
+  bool base_recorded = false;
+  std::vector<std::array<float, 7>> tl;
+  long long trace_launches = 0;  // tiled launches so far (the timeline keeps the last T_TRACE_LAUNCHES)
+  int trace_n[T_TRACE_LAUNCHES] = {0};
   std::atomic<int64_t> next_ticket{0};
   cudaEvent_t ev_last_conv_ref = nullptr;  // ev_conv of the previous block's slot (history dependency)
   bool have_last_conv = false;
@@ -308,6 +325,7 @@ static void slot_free(Slot &s) {
 static int drain(xlg_group *g) {
   CU_OK(cudaStreamSynchronize(g->s_in));
   CU_OK(cudaStreamSynchronize(g->s_ph));
+  CU_OK(cudaStreamSynchronize(g->s_cv));
   for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamSynchronize(g->s_cs[i]));
   CU_OK(cudaStreamSynchronize(g->s_out));
   return 0;
@@ -316,6 +334,17 @@ static int drain(xlg_group *g) {
 static void harvest_locked(xlg_group *g, Slot &s) {
   if (s.harvested) return;
   s.harvested = true;
+  if (g->timeline && g->base_recorded && s.pf_conv && s.pf_phase && s.pf_tile) {
+    std::array<float, 7> r;
+    r[0] = (float)s.ticket.load();
+    const int par = (int)((s.ticket.load() / XLG_SLOTS) & 1);
+    for (int i = 0; i < 6; i++) {
+      cudaEvent_t e = (i == 2 || i == 3) ? s.tl_ph[par][i - 2] : s.pf[i];
+      if (cudaEventElapsedTime(&r[1 + i], g->ev_base, e) != cudaSuccess) r[1 + i] = -1.f;
+    }
+    g->tl.push_back(r);
+    cudaGetLastError();
+  }
   if (!g->profiling) return;
   float ms = 0;
   if (s.pf_conv && cudaEventElapsedTime(&ms, s.pf[0], s.pf[1]) == cudaSuccess) {
@@ -618,9 +647,21 @@ static int rebuild_layout(xlg_group *g) {
       h.kind = m.as_long ? 2 : 1;
       const size_t gi = sl / T_CG, mslot = sl % T_CG;
       float2 *dst = tile_taps.data() + base + gi * (size_t)m.L * T_CG;
-      for (size_t j = 0; j < T; j++) {
-        const size_t f = (j / D) * m.Dp + (j % D);
-        dst[f * T_CG + mslot] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+      if (g->packed && !m.as_long) {
+        // packed kernel: a client PAIR's tap is (re0, re1, im0, im1) -- one 128-bit load = two FFMA2 operands
+        float *dq = reinterpret_cast<float *>(dst);
+        const size_t pair = mslot / 2, e = mslot % 2;
+        for (size_t j = 0; j < T; j++) {
+          const size_t f = (j / D) * m.Dp + (j % D);
+          float *q4 = dq + (f * T_CG + 2 * pair) * 2;
+          q4[e] = h.rev[2 * j];
+          q4[2 + e] = h.rev[2 * j + 1];
+        }
+      } else {
+        for (size_t j = 0; j < T; j++) {
+          const size_t f = (j / D) * m.Dp + (j % D);
+          dst[f * T_CG + mslot] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+        }
       }
     }
     dest.push_back(ch);
@@ -859,13 +900,14 @@ static void partition_create(xlg_group *g, int device) {
   CUdevResource all, small, rest;
   unsigned int groups = 1;
   CUdevResourceDesc d_small = nullptr, d_rest = nullptr;
-  CUstream st_ph = nullptr, st_c[xlg_group::kMaxCs] = {nullptr, nullptr, nullptr, nullptr};
+  CUstream st_ph = nullptr, st_cv = nullptr, st_c[xlg_group::kMaxCs] = {nullptr, nullptr, nullptr, nullptr};
   if (p_devget(&dev, device) != CUDA_SUCCESS || p_getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
       p_split(&small, &groups, &all, &rest, 0, (unsigned)want_sms) != CUDA_SUCCESS || groups != 1 ||
       p_desc(&d_small, &small, 1) != CUDA_SUCCESS || p_desc(&d_rest, &rest, 1) != CUDA_SUCCESS ||
       p_create(&g->part.small_ctx, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
       p_create(&g->part.big_ctx, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
       p_stream(&st_ph, g->part.small_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+      p_stream(&st_cv, g->part.small_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
       p_stream(&st_c[0], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
       p_stream(&st_c[1], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
       p_stream(&st_c[2], g->part.big_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
@@ -877,6 +919,7 @@ static void partition_create(xlg_group *g, int device) {
   g->part.small_sms = (int)small.sm.smCount;
   g->part.big_sms = (int)rest.sm.smCount;
   g->s_ph = (cudaStream_t)st_ph;
+  g->s_cv = (cudaStream_t)st_cv;
   for (int i = 0; i < xlg_group::kMaxCs; i++) g->s_cs[i] = (cudaStream_t)st_c[i];
   g->part.ok = true;
 }
@@ -941,6 +984,9 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     return fail(-EIO);
   if (!g->part.ok) {
     if (cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
+    int prio_lo = 0, prio_hi = 0;  // "greatest" priority is the numerically lowest
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_lo = prio_hi = 0;
+    if (cudaStreamCreateWithPriority(&g->s_cv, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(-EIO);
     for (int i = 0; i < xlg_group::kMaxCs; i++)
       if (cudaStreamCreateWithFlags(&g->s_cs[i], cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
   }
@@ -959,22 +1005,34 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
   {
     const char *tv = getenv("XLATING_B200_TILE");
     if (tv != nullptr) g->tile_force = atoi(tv);
+    const char *pk = getenv("XLATING_B200_FFMA2");
+    if (pk != nullptr) g->packed = atoi(pk) != 0;  // A/B: scalar FFMA (0) or packed FFMA2 (1) tiled kernel
     const char *lv = getenv("XLATING_B200_LONG");
     if (lv != nullptr && atoi(lv) >= 1 && atoi(lv) <= 4) g->long_gen = atoi(lv);  // A/B of the long-filter kernels
     if (g->long_gen == 1) g->long_kt = W_KT;
+    const char *cvs = getenv("XLATING_B200_CONV_STREAM");
+    if (cvs != nullptr) g->conv_own_stream = atoi(cvs) != 0;
     const char *sv = getenv("XLATING_B200_SPECULATE");
     if (sv != nullptr) g->speculate = atoi(sv) != 0;
     const char *cv = getenv("XLATING_B200_CSTREAMS");
     if (cv != nullptr) g->n_cs = std::min(std::max(atoi(cv), 1), (int)xlg_group::kMaxCs);
     g->fir_sms = g->part.ok ? g->part.big_sms : prop.multiProcessorCount;
   }
-  if (cudaFuncSetAttribute(fir_tile_cf32_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+  if (cudaFuncSetAttribute(fir_tile_cf32_kernel<32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
-      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
+          cudaSuccess ||
+      cudaFuncSetAttribute(fir_tile_cf32_kernel<16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
       cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fir_long2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM) != cudaSuccess ||
@@ -983,8 +1041,15 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
+  if (getenv("XLATING_B200_TIMELINE") != nullptr && cudaEventCreate(&g->ev_base) == cudaSuccess) {
+    g->timeline = true;
+    for (Slot &sl : g->slots)
+      for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++)
+          if (cudaEventCreate(&sl.tl_ph[a][b]) != cudaSuccess) g->timeline = false;
+  }
   if (getenv("XLATING_B200_TRACE") != nullptr && atoi(getenv("XLATING_B200_TRACE")) != 0) {
-    if (cudaMalloc(&g->d_trace, sizeof(long long) * 4 * 16384) != cudaSuccess) g->d_trace = nullptr;
+    if (cudaMalloc(&g->d_trace, sizeof(long long) * T_TRACE_REC * T_TRACE_CTAS * T_TRACE_LAUNCHES) != cudaSuccess) g->d_trace = nullptr;
   }
   rc = ensure_ring(g, 4096, false);
   if (rc) return fail(rc);
@@ -997,23 +1062,36 @@ extern "C" void xlg_destroy(xlg_group *g) {
   cudaSetDevice(g->device);
   if (g->s_in) cudaStreamSynchronize(g->s_in);
   if (g->s_ph) cudaStreamSynchronize(g->s_ph);
+  if (g->s_cv) cudaStreamSynchronize(g->s_cv);
   for (cudaStream_t st : g->s_cs)
     if (st) cudaStreamSynchronize(st);
   if (g->s_out) cudaStreamSynchronize(g->s_out);
+  if (g->timeline) {
+    for (Slot &sl : g->slots)
+      if (sl.ticket.load() >= 0) harvest_locked(g, sl);
+    FILE *f = fopen(getenv("XLATING_B200_TIMELINE") ? getenv("XLATING_B200_TIMELINE") : "/dev/null", "w");
+    if (f != nullptr) {
+      fprintf(f, "# ticket conv_ready conv_done phase_start phase_done fir_ready fir_done   (ms since the first submit)\n");
+      for (const auto &r : g->tl)
+        fprintf(f, "%.0f %.4f %.4f %.4f %.4f %.4f %.4f\n", r[0], r[1], r[2], r[3], r[4], r[5], r[6]);
+      fclose(f);
+    }
+    cudaEventDestroy(g->ev_base);
+  }
   if (g->d_trace != nullptr && g->trace_ctas <= 0) cudaFree(g->d_trace);
   if (g->d_trace != nullptr && g->trace_ctas > 0) {
-    // timeline of the LAST tiled launch: mean cycles per CTA in each phase
-    std::vector<long long> t((size_t)4 * g->trace_ctas);
+    // timeline of the last T_TRACE_LAUNCHES tiled launches; the summary line is about the newest one
+    std::vector<long long> t((size_t)T_TRACE_REC * T_TRACE_CTAS * T_TRACE_LAUNCHES);
     if (cudaMemcpy(t.data(), g->d_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const int slot = (int)((g->trace_launches - 1) % T_TRACE_LAUNCHES);
+      const long long *r = t.data() + (size_t)slot * T_TRACE_REC * T_TRACE_CTAS;
       double stage = 0, loop = 0, epi = 0;
-      long long first = t[0], last = t[3];
       for (int i = 0; i < g->trace_ctas; i++) {
-        const long long t2 = (t[4 * i + 2] & 0x0000ffffffffffffll) | (t[4 * i + 1] & ~0x0000ffffffffffffll);
-        stage += (double)(t[4 * i + 1] - t[4 * i]);
-        loop += (double)(t2 - t[4 * i + 1]);
-        epi += (double)(t[4 * i + 3] - t2);
-        first = std::min(first, t[4 * i]);
-        last = std::max(last, t[4 * i + 3]);
+        const long long *e = r + (size_t)T_TRACE_REC * i;
+        const long long t2 = (e[2] & 0x0000ffffffffffffll) | (e[1] & ~0x0000ffffffffffffll);
+        stage += (double)(e[1] - e[0]);
+        loop += (double)(t2 - e[1]);
+        epi += (double)(e[3] - t2);
       }
       const double n = g->trace_ctas;
       fprintf(stderr, "xlating_b200 trace: %d CTAs, mean cycles stage %.0f loop %.0f epilogue %.0f (%.1f%% / %.1f%% / %.1f%%)\n",
@@ -1021,8 +1099,12 @@ extern "C" void xlg_destroy(xlg_group *g) {
               100 * loop / (stage + loop + epi), 100 * epi / (stage + loop + epi));
       const char *path = getenv("XLATING_B200_TRACE_FILE");
       if (path != nullptr) {
+        // header: record length, CTAs per launch slot, launch slots, launches so far, CTAs of each slot
         FILE *f = fopen(path, "wb");
         if (f != nullptr) {
+          long long hdr[4 + T_TRACE_LAUNCHES] = {T_TRACE_REC, T_TRACE_CTAS, T_TRACE_LAUNCHES, g->trace_launches};
+          for (int i = 0; i < T_TRACE_LAUNCHES; i++) hdr[4 + i] = g->trace_n[i];
+          fwrite(hdr, sizeof(long long), 4 + T_TRACE_LAUNCHES, f);
           fwrite(t.data(), sizeof(long long), t.size(), f);
           fclose(f);
         }
@@ -1064,6 +1146,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_order) cudaFree(g->d_order);
   if (g->s_in) cudaStreamDestroy(g->s_in);
   if (g->s_ph) cudaStreamDestroy(g->s_ph);
+  if (g->s_cv) cudaStreamDestroy(g->s_cv);
   for (cudaStream_t st : g->s_cs)
     if (st) cudaStreamDestroy(st);
   if (g->s_out) cudaStreamDestroy(g->s_out);
@@ -1169,10 +1252,15 @@ template <int FMT>
 static void launch_convert(bool q15, const void *raw, xlg_group *g, long long S, int n, cudaStream_t st) {
   const int threads = 256, blocks = (n + threads - 1) / threads;
   const unsigned mask = (unsigned)(g->ring_cap - 1);
-  if (q15)
+  const size_t pair_bytes = FMT == 2 ? 8 : 4;
+  if (q15) {
     convert_q15_kernel<FMT><<<blocks, threads, 0, st>>>(raw, g->qring, mask, S, n);
-  else
+  } else if ((n & 1) == 0 && (S & 1) == 0 && ((uintptr_t)raw % pair_bytes) == 0) {
+    const int per_cta = threads * CV_STEPS * 2;
+    convert_cf32_vec_kernel<FMT><<<(n + per_cta - 1) / per_cta, threads, 0, st>>>(raw, g->ring, mask, S, n);
+  } else {
     convert_cf32_kernel<FMT><<<blocks, threads, 0, st>>>(raw, g->ring, mask, S, n);
+  }
 }
 
 extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t input_len, uint32_t flags) {
@@ -1274,6 +1362,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
   // cannot fill 148 SMs evenly); per-kernel profiling keeps a single stream so
   // that event-timed durations are not inflated by the overlap
   cudaStream_t cs = g->profiling ? g->s_cs[0] : g->s_cs[ticket % g->n_cs];
+  cudaStream_t cvs = g->conv_own_stream ? g->s_cv : cs;  // stream of the raw -> ring conversion
 
   // ---- input staging ----
   const void *d_in = input;
@@ -1292,7 +1381,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     }
     CU_OK(cudaMemcpyAsync(s.d_raw, src, bytes, cudaMemcpyHostToDevice, g->s_in));
     CU_OK(cudaEventRecord(s.ev_h2d, g->s_in));
-    CU_OK(cudaStreamWaitEvent(cs, s.ev_h2d, 0));
+    CU_OK(cudaStreamWaitEvent(cvs, s.ev_h2d, 0));
     // caller-owned pinned memory is read by the copy engine AFTER this call returns: unless
     // the caller promised to leave it alone (XLG_INPUT_KEEP), wait for the copy (a 256 KiB
     // block is ~10 us) so that the buffer may be reused at once, like a pageable one
@@ -1300,34 +1389,40 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     d_in = s.d_raw;
   }
 
-  // ---- convert (compute stream) ----
+  // ---- convert (its own stream: never behind the FIR CTAs of earlier blocks that still wait for an SM) ----
   s.pf_conv = s.pf_phase = s.pf_tile = s.pf_gen = false;
   if (n > 0) {
-    if (g->profiling) {
-      CU_OK(cudaEventRecord(s.pf[0], cs));
+    if (g->timeline && !g->base_recorded) {
+      CU_OK(cudaEventRecord(g->ev_base, cvs));
+      g->base_recorded = true;
+    }
+    if (g->profiling || g->timeline) {
+      CU_OK(cudaEventRecord(s.pf[0], cvs));
       s.pf_conv = true;
     }
     if (fmt == XLG_FMT_CU8)
-      launch_convert<0>(q15, d_in, g, S, n, cs);
+      launch_convert<0>(q15, d_in, g, S, n, cvs);
     else if (fmt == XLG_FMT_CS8)
-      launch_convert<1>(q15, d_in, g, S, n, cs);
+      launch_convert<1>(q15, d_in, g, S, n, cvs);
     else
-      launch_convert<2>(q15, d_in, g, S, n, cs);
-    if (g->profiling) CU_OK(cudaEventRecord(s.pf[1], cs));
-    CU_OK(cudaEventRecord(s.ev_conv, cs));
+      launch_convert<2>(q15, d_in, g, S, n, cvs);
+    if (g->profiling || g->timeline) CU_OK(cudaEventRecord(s.pf[1], cvs));
+    CU_OK(cudaEventRecord(s.ev_conv, cvs));
   }
+  // the FIR reads this block's samples and, as history, the previous blocks'
   if (g->have_last_conv) CU_OK(cudaStreamWaitEvent(cs, g->ev_last_conv_ref, 0));
   if (n > 0) {
+    if (cvs != cs) CU_OK(cudaStreamWaitEvent(cs, s.ev_conv, 0));
     g->ev_last_conv_ref = s.ev_conv;
     g->have_last_conv = true;
   }
 
   // ---- oscillator pre-pass (own stream: chains only on the previous pre-pass) ----
   if (nc > 0) {
-    if (g->profiling) {
-      CU_OK(cudaEventRecord(s.pf[2], g->s_ph));
-      s.pf_phase = true;
-    }
+    const bool tl_phase = g->timeline && !(g->spec_valid && !q15);  // a pre-pass that ran ahead was stamped then
+    if (g->profiling) CU_OK(cudaEventRecord(s.pf[2], g->s_ph));
+    if (tl_phase) CU_OK(cudaEventRecord(s.tl_ph[(ticket / XLG_SLOTS) & 1][0], g->s_ph));
+    if (g->profiling || g->timeline) s.pf_phase = true;
     bool ran_ahead = false;
     if (q15) {
       phase_q15_kernel<<<(nc + P_QTHREADS - 1) / P_QTHREADS, P_QTHREADS, 0, g->s_ph>>>(g->d_clients, nc, s.d_blk,
@@ -1343,6 +1438,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
                                                                    s.d_endph, nullptr, S, n);
     }
     if (g->profiling) CU_OK(cudaEventRecord(s.pf[3], g->s_ph));
+    if (tl_phase) CU_OK(cudaEventRecord(s.tl_ph[(ticket / XLG_SLOTS) & 1][1], g->s_ph));
     if (!ran_ahead) CU_OK(cudaEventRecord(s.ev_phase, g->s_ph));
     CU_OK(cudaStreamWaitEvent(cs, s.ev_phase, 0));
     // ... and the NEXT block's pre-pass, assuming it is as long as this one
@@ -1350,8 +1446,10 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       Slot &ns = g->slots[(ticket + 1) % XLG_SLOTS];
       if (ns.ticket.load() >= 0) CU_OK(cudaStreamWaitEvent(g->s_ph, ns.ev_done, 0));  // its tables are still in use
       // (the kernel itself saves every client's state before it advances it: no copy on the critical path)
+      if (g->timeline) CU_OK(cudaEventRecord(ns.tl_ph[((ticket + 1) / XLG_SLOTS) & 1][0], g->s_ph));
       phase_cf32_kernel<<<g->n_order / 32, P_THREADS, 0, g->s_ph>>>(g->d_clients, g->d_order, ns.d_blk, ns.d_phases,
                                                                    ns.d_endph, g->d_clients_backup, S + n, n);
+      if (g->timeline) CU_OK(cudaEventRecord(ns.tl_ph[((ticket + 1) / XLG_SLOTS) & 1][1], g->s_ph));
       CU_OK(cudaEventRecord(ns.ev_phase, g->s_ph));
       g->spec_valid = true;
       g->spec_S = S + n;
@@ -1422,27 +1520,42 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       s.tile_macs += (uint64_t)k.tiles * KT * (uint64_t)k.L * (uint64_t)ch.members.size();
     }
     if (ctas > 0) {
-      if (g->profiling) {
+      if (g->profiling || g->timeline) {
         CU_OK(cudaEventRecord(s.pf[4], cs));
         s.pf_tile = true;
       }
       const float2 *tt = (const float2 *)g->d_tile_taps;
-#define XL_LAUNCH_TILE(LO_, RK_)                                                                              \
-  fir_tile_cf32_kernel<LO_, RK_><<<ctas, TileShape<LO_, RK_>::kThreads, smem, cs>>>(P, g->ring, mask, tt,      \
+      long long *trace_ptr = nullptr;
+      if (g->d_trace != nullptr && ctas <= T_TRACE_CTAS) {
+        const int tslot = (int)(g->trace_launches % T_TRACE_LAUNCHES);
+        trace_ptr = g->d_trace + (size_t)tslot * T_TRACE_REC * T_TRACE_CTAS;
+        g->trace_n[tslot] = ctas;
+        g->trace_launches++;
+        g->trace_ctas = ctas;
+      }
+#define XL_LAUNCH_TILE(LO_, RK_, PK_)                                                                              \
+  fir_tile_cf32_kernel<LO_, RK_, PK_><<<ctas, TileShape<LO_, RK_>::kThreads, smem, cs>>>(P, g->ring, mask, tt, \
                                                                                   g->d_members, g->d_member_cid, \
                                                                                   g->d_member_incr, s.d_blk,   \
-                                                                                  s.d_phases, s.d_out, g->d_trace)
+                                                                                  s.d_phases, s.d_out, trace_ptr)
+#define XL_LAUNCH_TILE_PK(LO_, RK_) \
+  do {                             \
+    if (g->packed)                 \
+      XL_LAUNCH_TILE(LO_, RK_, true);  \
+    else                           \
+      XL_LAUNCH_TILE(LO_, RK_, false); \
+  } while (0)
       if (lo == 32 && rk == 4)
-        XL_LAUNCH_TILE(32, 4);
+        XL_LAUNCH_TILE_PK(32, 4);
       else if (lo == 16 && rk == 4)
-        XL_LAUNCH_TILE(16, 4);
+        XL_LAUNCH_TILE_PK(16, 4);
       else if (lo == 16 && rk == 2)
-        XL_LAUNCH_TILE(16, 2);
+        XL_LAUNCH_TILE_PK(16, 2);
       else
-        XL_LAUNCH_TILE(16, 1);
+        XL_LAUNCH_TILE_PK(16, 1);
+#undef XL_LAUNCH_TILE_PK
 #undef XL_LAUNCH_TILE
-      if (g->d_trace != nullptr) g->trace_ctas = std::min(ctas, 16384);
-      if (g->profiling) CU_OK(cudaEventRecord(s.pf[5], cs));
+      if (g->profiling || g->timeline) CU_OK(cudaEventRecord(s.pf[5], cs));
     }
   }
   // ---- long filters: split-K partial sums, then the ordered reduction ----
@@ -1707,6 +1820,7 @@ extern "C" int xlg_wait_stream(xlg_group *g, void *cuda_stream) {
   CU_OK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
   for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamWaitEvent(g->s_cs[i], ev, 0));
   CU_OK(cudaStreamWaitEvent(g->s_in, ev, 0));
+  CU_OK(cudaStreamWaitEvent(g->s_cv, ev, 0));
   CU_OK(cudaEventDestroy(ev));
   return 0;
 }
@@ -1720,6 +1834,7 @@ extern "C" int xlg_timer_start(xlg_group *g) {
   CU_OK(cudaStreamWaitEvent(g->s_in, g->ev_t0, 0));
   for (int i = 1; i < g->n_cs; i++) CU_OK(cudaStreamWaitEvent(g->s_cs[i], g->ev_t0, 0));
   CU_OK(cudaStreamWaitEvent(g->s_ph, g->ev_t0, 0));
+  CU_OK(cudaStreamWaitEvent(g->s_cv, g->ev_t0, 0));
   CU_OK(cudaStreamWaitEvent(g->s_out, g->ev_t0, 0));
   return 0;
 }
@@ -1730,9 +1845,9 @@ extern "C" int xlg_timer_stop(xlg_group *g, float *elapsed_ms) {
   // s_out's last event already depends on the FIR of the last block; add the others
   cudaEvent_t ev;
   CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  cudaStream_t others[2 + xlg_group::kMaxCs] = {g->s_in, g->s_ph};
-  for (int i = 0; i < g->n_cs; i++) others[2 + i] = g->s_cs[i];
-  for (int oi = 0; oi < 2 + g->n_cs; oi++) {
+  cudaStream_t others[3 + xlg_group::kMaxCs] = {g->s_in, g->s_ph, g->s_cv};
+  for (int i = 0; i < g->n_cs; i++) others[3 + i] = g->s_cs[i];
+  for (int oi = 0; oi < 3 + g->n_cs; oi++) {
     cudaStream_t st = others[oi];
     CU_OK(cudaEventRecord(ev, st));
     CU_OK(cudaStreamWaitEvent(g->s_out, ev, 0));

@@ -90,6 +90,35 @@ __global__ void convert_cf32_kernel(const void *__restrict__ raw, float2 *__rest
   ring[(unsigned)((unsigned long long)(S + i)) & mask] = v;
 }
 
+// The same conversion, two samples per thread and step (one 4- or 8-byte load, one 16-byte store, both
+// coalesced across the warp), CV_STEPS steps per thread: 8x fewer CTAs -- one wave even on the 8 SMs of
+// the oscillator partition, where the conversion runs so that it never queues behind FIR CTAs.  Needs an even
+// sample count, an even stream position and a raw pointer aligned to two samples (the launcher checks).
+constexpr int CV_STEPS = 4;
+template <int FMT>
+__global__ void convert_cf32_vec_kernel(const void *__restrict__ raw, float2 *__restrict__ ring, unsigned mask,
+                                        long long S, int n) {
+  const int pairs = n >> 1;
+  int p = blockIdx.x * (blockDim.x * CV_STEPS) + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < CV_STEPS; j++, p += blockDim.x) {
+    if (p >= pairs) return;
+    float4 v;
+    if (FMT == 0) {
+      const uchar4 u = reinterpret_cast<const uchar4 *>(raw)[p];
+      v = make_float4(cvt_cu8_f32(u.x), cvt_cu8_f32(u.y), cvt_cu8_f32(u.z), cvt_cu8_f32(u.w));
+    } else if (FMT == 1) {
+      const char4 u = reinterpret_cast<const char4 *>(raw)[p];
+      v = make_float4(cvt_cs8_f32(u.x), cvt_cs8_f32(u.y), cvt_cs8_f32(u.z), cvt_cs8_f32(u.w));
+    } else {
+      const short4 u = reinterpret_cast<const short4 *>(raw)[p];
+      v = make_float4(cvt_cs16_f32(u.x), cvt_cs16_f32(u.y), cvt_cs16_f32(u.z), cvt_cs16_f32(u.w));
+    }
+    const unsigned idx = (unsigned)((unsigned long long)(S + 2ll * p)) & mask;  // even: the pair never straddles the wrap
+    *reinterpret_cast<float4 *>(ring + idx) = v;
+  }
+}
+
 template <int FMT>
 __global__ void convert_q15_kernel(const void *__restrict__ raw, short2 *__restrict__ ring,
                                    unsigned mask, long long S, int n) {
@@ -235,16 +264,28 @@ fir_generic_q15_kernel(const ClientDev *__restrict__ cl, const BlkInfo *__restri
 // ---------------------------------------------------------------------------
 constexpr int T_RC = 8;              // clients per thread
 constexpr int T_CG = 32;             // clients per CTA
-constexpr int T_JC = 32;             // flat taps per TMA chunk
-constexpr int T_STAGES = 3;
+#ifndef XL_TILE_JC
+#define XL_TILE_JC 32
+#endif
+#ifndef XL_TILE_STAGES
+#define XL_TILE_STAGES 3
+#endif
+#ifndef XL_TILE_MINCTAS
+#define XL_TILE_MINCTAS 4
+#endif
+constexpr int T_JC = XL_TILE_JC;     // flat taps per TMA chunk (multiple of 8)
+constexpr int T_STAGES = XL_TILE_STAGES;
 #ifndef XL_TILE_UNROLL
 #define XL_TILE_UNROLL 8
 #endif
 constexpr int T_UNROLL = XL_TILE_UNROLL;  // taps per unrolled inner-loop body (L is a multiple of 8)
 constexpr int T_CHUNK_F2 = T_JC * T_CG;       // float2 per chunk (1024)
 constexpr int T_CHUNK_BYTES = T_CHUNK_F2 * 8;  // 8 KiB
-constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + 64;  // tap stages + mbarriers
+constexpr int T_SMEM_FIXED = T_STAGES * T_CHUNK_BYTES + ((2 * T_STAGES + 1) * 8 + 63) / 64 * 64;  // tap stages + mbarriers
 constexpr int T_MAX_CLASSES = 36;    // (D, T) classes per launch: 36 x 104 bytes stays inside the classic 4 KiB parameter space
+constexpr int T_TRACE_REC = 6;       // long long per CTA in the XLATING_B200_TRACE timeline
+constexpr int T_TRACE_LAUNCHES = 16; // launches kept (ring)
+constexpr int T_TRACE_CTAS = 4096;   // CTAs recorded per launch
 constexpr int T_RK_LONG = 4;         // outputs per thread in the long-filter kernel
 
 // Shape of the tile a CTA computes.  LO = number of output lanes in a warp, RK =
@@ -265,7 +306,7 @@ struct TileShape {
   static constexpr int kWarps = T_CG / kWarpClients;         // 4 or 2
   static constexpr int kThreads = kWarps * 32;               // 128 or 64
   static constexpr int kKT = LO * RK;                        // outputs per CTA
-  static constexpr int kMinCtas = LO == 32 ? 3 : 4;          // shared memory allows 4 CTAs per SM: up to 255 registers
+  static constexpr int kMinCtas = LO == 32 ? 3 : XL_TILE_MINCTAS;  // CTAs per SM the register budget is set for
 };
 
 // One class = clients with identical (D, T, window alignment).  "Flat" tap index:
@@ -350,7 +391,29 @@ __device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-template <int LO, int RK>
+// packed FP32 pairs (sm_100 FFMA2): one issue slot, two FMA-pipe cycles -- the shared
+// loads and the loop's integer work then issue in the slots the FMAs no longer need
+typedef unsigned long long u64x;
+__device__ __forceinline__ u64x ffma2(u64x a, u64x b, u64x c) {
+  u64x d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64x pack2f(float lo, float hi) {
+  u64x r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(u64x v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// PK = packed arithmetic: the taps of a client PAIR are stored (re0, re1, im0, im1) so that
+// one 128-bit shared load yields the two packed operands TR = (re0, re1), TI = (im0, im1);
+// per pair and output the four FMAs of the scalar kernel become four FFMA2 on
+// RE = (re of client 0, re of client 1) and IM likewise, in the SAME order per accumulator
+// (+xr*tr, -xi*ti | +xr*ti, +xi*tr): results are bit-identical to PK = false.
+template <int LO, int RK, bool PK>
 __global__ void __launch_bounds__(TileShape<LO, RK>::kThreads, TileShape<LO, RK>::kMinCtas)
 fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
                      const float2 *__restrict__ tile_taps, const int *__restrict__ member_off,
@@ -475,10 +538,14 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
   if (trace != nullptr) tr1 = clock64();
 
   float2 acc[RK][T_RC];
+  u64x RE[RK][T_RC / 2], IM[RK][T_RC / 2];  // PK only
 #pragma unroll
-  for (int i = 0; i < RK; i++)
+  for (int i = 0; i < RK; i++) {
 #pragma unroll
     for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < T_RC / 2; q++) RE[i][q] = IM[i][q] = 0ull;
+  }
 
   const float2 *xb[RK];
 #pragma unroll
@@ -496,24 +563,43 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
 #pragma unroll
         for (int u = 0; u < T_UNROLL; u++) {
           float2 x[RK];
-          float4 tq[T_RC / 2];
 #pragma unroll
           for (int i = 0; i < RK; i++) x[i] = xb[i][fbase + f + u];
+          if constexpr (PK) {
+            ulonglong2 tq[T_RC / 2];  // .x = (re0, re1), .y = (im0, im1)
 #pragma unroll
-          for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+            for (int q = 0; q < T_RC / 2; q++)
+              tq[q] = reinterpret_cast<const ulonglong2 *>(tp)[(f + u) * (T_CG / 2) + q];
 #pragma unroll
-          for (int i = 0; i < RK; i++) {
+            for (int i = 0; i < RK; i++) {
+              const u64x XR = pack2f(x[i].x, x[i].x), XI = pack2f(x[i].y, x[i].y);
+              const u64x XN = XI ^ 0x8000000080000000ull;
 #pragma unroll
-            for (int q = 0; q < T_RC / 2; q++) {
-              float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
-              a0.x = fmaf(x[i].x, tq[q].x, a0.x);
-              a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
-              a0.y = fmaf(x[i].x, tq[q].y, a0.y);
-              a0.y = fmaf(x[i].y, tq[q].x, a0.y);
-              a1.x = fmaf(x[i].x, tq[q].z, a1.x);
-              a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
-              a1.y = fmaf(x[i].x, tq[q].w, a1.y);
-              a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+              for (int q = 0; q < T_RC / 2; q++) {
+                RE[i][q] = ffma2(XR, tq[q].x, RE[i][q]);
+                RE[i][q] = ffma2(XN, tq[q].y, RE[i][q]);
+                IM[i][q] = ffma2(XR, tq[q].y, IM[i][q]);
+                IM[i][q] = ffma2(XI, tq[q].x, IM[i][q]);
+              }
+            }
+          } else {
+            float4 tq[T_RC / 2];
+#pragma unroll
+            for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+            for (int i = 0; i < RK; i++) {
+#pragma unroll
+              for (int q = 0; q < T_RC / 2; q++) {
+                float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+                a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+                a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+                a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+                a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+                a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+                a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+                a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+                a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+              }
             }
           }
         }
@@ -533,6 +619,15 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     }
   }
 
+  if constexpr (PK) {
+#pragma unroll
+    for (int i = 0; i < RK; i++)
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++) {
+        unpack2f(RE[i][q], acc[i][2 * q].x, acc[i][2 * q + 1].x);
+        unpack2f(IM[i][q], acc[i][2 * q].y, acc[i][2 * q + 1].y);
+      }
+  }
   if (trace != nullptr) tr2 = clock64();
   // epilogue: derotate with the pre-computed oscillator and store (coalesced in k).
   // The oscillator table is [k][32 clients]: this thread's 8 clients are 64
@@ -584,13 +679,18 @@ fir_tile_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restr
     }
   }
   if (trace != nullptr && tid == 0) {
-    long long *t = trace + 4 * (size_t)blockIdx.x;
-    unsigned smid;
+    long long *t = trace + T_TRACE_REC * (size_t)blockIdx.x;
+    unsigned smid, wid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     t[0] = tr0;
     t[1] = tr1;
     t[2] = (tr2 & 0x0000ffffffffffffll) | ((long long)smid << 48);  // smid in the top 16 bits
     t[3] = clock64();
+    t[4] = (long long)gt;                                          // ns at the END of the CTA
+    t[5] = ((long long)ci << 32) | ((long long)wid << 16) | (long long)(L & 0xffff);
   }
 }
 
