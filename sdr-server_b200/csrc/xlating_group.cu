@@ -244,6 +244,14 @@ struct xlg_group {
   void *d_tile_taps = nullptr;
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
   int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long3 / fir_long2) or 64 (XLATING_B200_LONG=1)
+  // long4's input strips through a TMA tensor map over the ring (XLATING_B200_LONG_TMAP=0: 28 bulk copies per stage)
+  bool long_tmap = true;
+  CUtensorMap strip_map;          // valid for (strip_ring, strip_cap, strip_D)
+  const void *strip_ring = nullptr;
+  size_t strip_cap = 0;
+  int strip_D = 0, strip_w = 0;   // strip_w: inner width of the map in samples (0 = could not be encoded)
+  bool long_pk_active = false;  // this layout's long classes ARE packed (packed_long, generation 4, every long D even)
+  bool packed_long = false;  // XLATING_B200_LONG_FFMA2=1: long4 on packed FFMA2 (long classes' taps packed per client pair)
   bool packed = false;    // XLATING_B200_FFMA2=1: tiled kernel on packed FFMA2 (bit-identical; measured 4-8 % slower in
                           // steady state); decides the tap packing too
   int long_gen = 4;       // XLATING_B200_LONG=1|2|3|4: which long-filter kernel (4 = pipelined 28 x 64 tile, the default)
@@ -583,6 +591,12 @@ static int rebuild_layout(xlg_group *g) {
     const bool merge = m.natural && !m.as_long && !getenv("XLATING_B200_NO_MERGE");
     buckets[std::make_tuple(h.D, h.T, merge ? -1ll : h.hist)].push_back(i);
   }
+  {
+    bool all_even = true;
+    for (auto &kv : buckets)
+      if (mode_of(std::get<0>(kv.first), std::get<1>(kv.first)).as_long && (std::get<0>(kv.first) & 1u)) all_even = false;
+    g->long_pk_active = g->packed_long && g->long_gen == 4 && all_even;
+  }
   std::vector<int> members;       // output row offset per member slot
   std::vector<int> member_cid;    // client id per member slot
   std::vector<float2> member_incr;
@@ -647,7 +661,7 @@ static int rebuild_layout(xlg_group *g) {
       h.kind = m.as_long ? 2 : 1;
       const size_t gi = sl / T_CG, mslot = sl % T_CG;
       float2 *dst = tile_taps.data() + base + gi * (size_t)m.L * T_CG;
-      if (g->packed && !m.as_long) {
+      if (m.as_long ? g->long_pk_active : g->packed) {
         // packed kernel: a client PAIR's tap is (re0, re1, im0, im1) -- one 128-bit load = two FFMA2 operands
         float *dq = reinterpret_cast<float *>(dst);
         const size_t pair = mslot / 2, e = mslot % 2;
@@ -924,6 +938,38 @@ static void partition_create(xlg_group *g, int device) {
   g->part.ok = true;
 }
 
+// Tensor map of the sample ring as rows of pitch D: element (c, r) = ring[r * D + c], 8-byte elements, box =
+// W_JSP x W4_KT (one stage's strips).  Rows overlap in memory when the inner width exceeds D; if the driver
+// refuses that, the map is D wide and boxes that would cross a row end fall back to per-strip copies.
+typedef CUresult (*pfn_cuTensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                               CUtensorMapFloatOOBfill);
+static void strip_map_update(xlg_group *g, int D) {
+  if (g->strip_ring == g->ring && g->strip_cap == g->ring_cap && g->strip_D == D) return;
+  g->strip_ring = g->ring;
+  g->strip_cap = g->ring_cap;
+  g->strip_D = D;
+  g->strip_w = 0;
+  pfn_cuTensorMapEncodeTiled enc;
+  if (!g->long_tmap || (D & 1) != 0 || (size_t)D + W_JSP >= g->ring_cap || !drv("cuTensorMapEncodeTiled", &enc)) return;
+  const cuuint32_t box[2] = {(cuuint32_t)W_JSP, (cuuint32_t)W4_KT}, estr[2] = {1, 1};
+  const cuuint64_t gstride[1] = {(cuuint64_t)D * 8};
+  for (int width : {D + W_JSP, D}) {
+    if (width < W_JSP) continue;
+    // rows up to the ring's end: the kernel only issues boxes that lie inside the ring (its own bound check),
+    // so the last rows' columns beyond the allocation are never touched
+    const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)(g->ring_cap / (size_t)D + 1)};
+    if (gdim[1] < (cuuint64_t)W4_KT) continue;
+    if (enc(&g->strip_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, g->ring, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      g->strip_w = width;
+      break;
+    }
+  }
+  if (g->strip_w == 0) XL_LOG("cuTensorMapEncodeTiled refused the strip map (D = %d); long filters use per-strip copies", D);
+}
+
 // ---------------------------------------------------------------------------
 // public API
 // ---------------------------------------------------------------------------
@@ -1012,6 +1058,10 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     if (g->long_gen == 1) g->long_kt = W_KT;
     const char *cvs = getenv("XLATING_B200_CONV_STREAM");
     if (cvs != nullptr) g->conv_own_stream = atoi(cvs) != 0;
+    const char *pl = getenv("XLATING_B200_LONG_FFMA2");
+    if (pl != nullptr) g->packed_long = atoi(pl) != 0;
+    const char *tm = getenv("XLATING_B200_LONG_TMAP");
+    if (tm != nullptr) g->long_tmap = atoi(tm) != 0;
     const char *sv = getenv("XLATING_B200_SPECULATE");
     if (sv != nullptr) g->speculate = atoi(sv) != 0;
     const char *cv = getenv("XLATING_B200_CSTREAMS");
@@ -1037,7 +1087,10 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
       cudaFuncSetAttribute(fir_long_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fir_long2_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(fir_long3_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(fir_long4_cf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(fir_long4_cf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fir_long4_cf32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fir_long4_cf32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fir_long4_cf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) {
     XL_LOG("cannot raise dynamic shared memory to %d bytes", kTileMaxSmem);
     return fail(-EIO);
   }
@@ -1573,7 +1626,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       const int n_out = ho.n_out[ch.real[0]];
       if (n_out <= 0) continue;
       const long long first = (S + n) - h0.hist - (long long)n_out * (long long)h0.D;
-      if (((first | (long long)h0.D) & 1) != 0) pipelined = false;
+      // (generation 4 fetches an odd window start from one sample earlier; generation 3 needs it even)
+      if ((h0.D & 1) != 0 || (!wide && (first & 1) != 0)) pipelined = false;
     }
     int n_live = 0;
     for (TileClassHost &ch : g->long_classes) n_live += ho.n_out[ch.real[0]] > 0 ? 1 : 0;
@@ -1613,9 +1667,23 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
         CU_OK(cudaEventRecord(s.pf[8], cs));
         s.pf_long = true;
       }
-      if (pipelined && wide)
-        fir_long4_cf32_kernel<<<ctas, W3_THREADS, W4_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
-                                                                s.d_partial);
+      if (pipelined && wide) {
+        // the first class gets the tensor map for its strips (all long clients of a stream normally share one D)
+        strip_map_update(g, P.cls[0].D);
+        P.cls[0].tmap_w = g->strip_w;
+#define XL_LAUNCH_LONG4(TM_, PK_)                                                                                  \
+  fir_long4_cf32_kernel<TM_, PK_><<<ctas, W3_THREADS, W4_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps, \
+                                                                    s.d_partial, g->strip_map)
+        if (g->strip_w > 0 && g->long_pk_active)
+          XL_LAUNCH_LONG4(true, true);
+        else if (g->strip_w > 0)
+          XL_LAUNCH_LONG4(true, false);
+        else if (g->long_pk_active)
+          XL_LAUNCH_LONG4(false, true);
+        else
+          XL_LAUNCH_LONG4(false, false);
+#undef XL_LAUNCH_LONG4
+      }
       else if (pipelined)
         fir_long3_cf32_kernel<<<ctas, W3_THREADS, W3_SMEM, cs>>>(P, g->ring, mask, (const float2 *)g->d_tile_taps,
                                                                 s.d_partial);

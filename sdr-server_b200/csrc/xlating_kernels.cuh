@@ -33,6 +33,7 @@
  */
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -335,7 +336,7 @@ struct TileClass {
   int nslab;           // partial-sum slabs the reduction adds: nseg, or ksplit for the pipelined kernel
   int ksplit;          // pipelined long-filter kernel: CTAs along the tap axis per (group, tile)
   int seg_per;         // ... and consecutive segments each of them walks
-  int pad2_;
+  int tmap_w;          // long4 with a TMA tensor map for the input strips: width of the map's inner dimension (0 = none)
 };
 
 struct TileLaunch {
@@ -385,6 +386,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// TMA 2-D tiled copy global -> shared through a tensor map (one instruction moves a whole box of rows)
+__device__ __forceinline__ void tma_tensor2d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
@@ -1174,13 +1183,21 @@ fir_long3_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__rest
 constexpr int W4_LO = 4;
 constexpr int W4_KT = W4_LO * W2_RK;    // 28 outputs per CTA
 constexpr int W4_GROUPS = 2;            // client groups per CTA
-constexpr int W4_STAGE_BYTES = W4_GROUPS * W_JS * T_CG * 8 + W4_KT * W_JSP * 8;  // 64 KiB taps + 28.4 KiB strips
+constexpr int W4_STAGE_BYTES = (W4_GROUPS * W_JS * T_CG * 8 + W4_KT * W_JSP * 8 + 127) / 128 * 128;  // 64 KiB taps + 28.4 KiB strips (128-byte aligned stages: TMA tensor destinations)
 constexpr int W4_SMEM = W3_STAGES * W4_STAGE_BYTES + 64;
 static_assert((W3_WARPS - 1) * 32 * W2_RK * T_RC * 2 * 4 <= W3_STAGES * W4_STAGE_BYTES, "reduction scratch reuses the stages");
 
+// TM = the 28 input strips of a stage arrive as ONE 2-D tensor copy (box 130 x 28 eight-byte elements, row
+// pitch D in the ring) instead of 28 bulk copies of 1 KiB: the stage loads, not the FMAs, are what this
+// kernel waits for (ncu: 12 % of warp time on the stage's mbarrier), and small copies cost ~300 cycles each.
+// A stage whose box would cross the ring's wrap-around (or the map's inner width) uses the strip path.
+// PK = packed FFMA2 arithmetic on client pairs, exactly as in fir_tile_cf32_kernel (taps packed
+// (re0, re1, im0, im1) by the host); same FMAs in the same order per accumulator: bit-identical.
+template <bool TM, bool PK>
 __global__ void __launch_bounds__(W3_THREADS, 1)
 fir_long4_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__restrict__ ring, unsigned mask,
-                      const float2 *__restrict__ tile_taps, float2 *__restrict__ partial) {
+                      const float2 *__restrict__ tile_taps, float2 *__restrict__ partial,
+                      const __grid_constant__ CUtensorMap strips) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W3_STAGES * W4_STAGE_BYTES);  // full[2], empty[2]
 
@@ -1214,31 +1231,52 @@ fir_long4_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__rest
   }
   __syncthreads();
 
+  const unsigned xoff = (unsigned)(K.first & 1);  // 1: strips start one sample early (see load_segment)
   auto load_segment = [&](int sg, int st) {
     const int f0 = sg * W_JS;
     const int len = min(W_JS, K.L - f0);
     float2 *ts = reinterpret_cast<float2 *>(smem + st * W4_STAGE_BYTES);
     float2 *xs = ts + W4_GROUPS * W_JS * T_CG;
-    const unsigned strip_bytes = (unsigned)len * 8u, tap_bytes = (unsigned)len * T_CG * 8u;
-    if (lane == 0) mbar_expect_tx(&bars[st], (unsigned)n_grp * tap_bytes + W4_KT * strip_bytes);
+    // bulk copies need 16-byte aligned sources: an odd window start (D is even, so every strip of every
+    // segment has the parity of K.first) is fetched from one sample earlier, two samples longer -- the row
+    // pitch W_JSP = W_JS + 2 has room -- and the readers skip the extra sample (xoff below)
+    const unsigned tap_bytes = (unsigned)len * T_CG * 8u;
+    const unsigned slen = (unsigned)len + 2u * xoff, strip_bytes = slen * 8u;
+    const long long w0 = K.first + (long long)k0 * D + f0 - (long long)xoff;
+    bool boxed = false;
+    unsigned q = 0, c0 = 0;
+    if (TM && K.tmap_w > 0) {
+      const unsigned idx0 = (unsigned)((unsigned long long)w0) & mask;
+      q = idx0 / (unsigned)D;
+      c0 = idx0 - q * (unsigned)D;
+      boxed = (unsigned long long)idx0 + (unsigned long long)(W4_KT - 1) * D + W_JSP <= (unsigned long long)mask + 1ull &&
+              c0 + (unsigned)W_JSP <= (unsigned)K.tmap_w;
+    }
+    if (lane == 0)
+      mbar_expect_tx(&bars[st], (unsigned)n_grp * tap_bytes + (boxed ? (unsigned)(W4_KT * W_JSP * 8) : W4_KT * strip_bytes));
     __syncwarp();
     if (lane < n_grp)
       tma_bulk_g2s(ts + lane * W_JS * T_CG, tile_taps + K.taps_off + ((long long)(grp0 + lane) * K.L + f0) * T_CG, tap_bytes,
                    &bars[st]);
-    const long long w0 = K.first + (long long)k0 * D + f0;
-    if (lane < W4_KT) {
+    if (boxed) {
+      if (lane == 0) tma_tensor2d_g2s(xs, &strips, (int)c0, (int)q, &bars[st]);
+    } else if (lane < W4_KT) {
       const unsigned idx = (unsigned)((unsigned long long)(w0 + (long long)lane * D)) & mask;
-      const unsigned n1 = min((unsigned)len, mask + 1u - idx);
+      const unsigned n1 = min(slen, mask + 1u - idx);
       tma_bulk_g2s(xs + lane * W_JSP, ring + idx, n1 * 8u, &bars[st]);
-      if (n1 < (unsigned)len) tma_bulk_g2s(xs + lane * W_JSP + n1, ring, ((unsigned)len - n1) * 8u, &bars[st]);
+      if (n1 < slen) tma_bulk_g2s(xs + lane * W_JSP + n1, ring, (slen - n1) * 8u, &bars[st]);
     }
   };
 
   float2 acc[W2_RK][T_RC];
+  u64x RE[W2_RK][T_RC / 2], IM[W2_RK][T_RC / 2];  // PK only
 #pragma unroll
-  for (int i = 0; i < W2_RK; i++)
+  for (int i = 0; i < W2_RK; i++) {
 #pragma unroll
     for (int c = 0; c < T_RC; c++) acc[i][c] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < T_RC / 2; q++) RE[i][q] = IM[i][q] = 0ull;
+  }
 
   if (seg_begin < seg_end) {
     if (warp == 0) load_segment(seg_begin, 0);
@@ -1257,31 +1295,50 @@ fir_long4_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__rest
         const float4 *tp = reinterpret_cast<const float4 *>(ts + gsel * W_JS * T_CG + cbase);
         const float2 *xb[W2_RK];
 #pragma unroll
-        for (int i = 0; i < W2_RK; i++) xb[i] = xs + (o + W4_LO * i) * W_JSP;
+        for (int i = 0; i < W2_RK; i++) xb[i] = xs + (o + W4_LO * i) * W_JSP + xoff;
         const int f_end = min(len, (warp + 1) * W3_JW);
 #pragma unroll 1
         for (int f = warp * W3_JW; f < f_end; f += T_UNROLL) {
 #pragma unroll
           for (int u = 0; u < T_UNROLL; u++) {
             float2 x[W2_RK];
-            float4 tq[T_RC / 2];
 #pragma unroll
             for (int i = 0; i < W2_RK; i++) x[i] = xb[i][f + u];
+            if constexpr (PK) {
+              ulonglong2 tq[T_RC / 2];  // .x = (re0, re1), .y = (im0, im1)
 #pragma unroll
-            for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+              for (int q = 0; q < T_RC / 2; q++)
+                tq[q] = reinterpret_cast<const ulonglong2 *>(tp)[(f + u) * (T_CG / 2) + q];
 #pragma unroll
-            for (int i = 0; i < W2_RK; i++) {
+              for (int i = 0; i < W2_RK; i++) {
+                const u64x XR = pack2f(x[i].x, x[i].x), XI = pack2f(x[i].y, x[i].y);
+                const u64x XN = XI ^ 0x8000000080000000ull;
 #pragma unroll
-              for (int q = 0; q < T_RC / 2; q++) {
-                float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
-                a0.x = fmaf(x[i].x, tq[q].x, a0.x);
-                a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
-                a0.y = fmaf(x[i].x, tq[q].y, a0.y);
-                a0.y = fmaf(x[i].y, tq[q].x, a0.y);
-                a1.x = fmaf(x[i].x, tq[q].z, a1.x);
-                a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
-                a1.y = fmaf(x[i].x, tq[q].w, a1.y);
-                a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+                for (int q = 0; q < T_RC / 2; q++) {
+                  RE[i][q] = ffma2(XR, tq[q].x, RE[i][q]);
+                  RE[i][q] = ffma2(XN, tq[q].y, RE[i][q]);
+                  IM[i][q] = ffma2(XR, tq[q].y, IM[i][q]);
+                  IM[i][q] = ffma2(XI, tq[q].x, IM[i][q]);
+                }
+              }
+            } else {
+              float4 tq[T_RC / 2];
+#pragma unroll
+              for (int q = 0; q < T_RC / 2; q++) tq[q] = tp[(f + u) * (T_CG / 2) + q];
+#pragma unroll
+              for (int i = 0; i < W2_RK; i++) {
+#pragma unroll
+                for (int q = 0; q < T_RC / 2; q++) {
+                  float2 &a0 = acc[i][2 * q], &a1 = acc[i][2 * q + 1];
+                  a0.x = fmaf(x[i].x, tq[q].x, a0.x);
+                  a0.x = fmaf(-x[i].y, tq[q].y, a0.x);
+                  a0.y = fmaf(x[i].x, tq[q].y, a0.y);
+                  a0.y = fmaf(x[i].y, tq[q].x, a0.y);
+                  a1.x = fmaf(x[i].x, tq[q].z, a1.x);
+                  a1.x = fmaf(-x[i].y, tq[q].w, a1.x);
+                  a1.y = fmaf(x[i].x, tq[q].w, a1.y);
+                  a1.y = fmaf(x[i].y, tq[q].z, a1.y);
+                }
               }
             }
           }
@@ -1290,6 +1347,15 @@ fir_long4_cf32_kernel(const __grid_constant__ TileLaunch P, const float2 *__rest
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[W3_STAGES + st]);  // this warp is done with the stage
     }
+  }
+  if constexpr (PK) {
+#pragma unroll
+    for (int i = 0; i < W2_RK; i++)
+#pragma unroll
+      for (int q = 0; q < T_RC / 2; q++) {
+        unpack2f(RE[i][q], acc[i][2 * q].x, acc[i][2 * q + 1].x);
+        unpack2f(IM[i][q], acc[i][2 * q].y, acc[i][2 * q + 1].y);
+      }
   }
   // warps 1..7 hand their sums to warp 0 through shared memory, layout [warp-1][value][lane]
   __syncthreads();

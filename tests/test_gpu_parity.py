@@ -390,6 +390,36 @@ def test_group_long_filter_split_k_kernel(pkg):
     g.close()
 
 
+@pytest.mark.parametrize("env", [{}, {"XLATING_B200_LONG_FFMA2": "1"}, {"XLATING_B200_LONG_TMAP": "0"},
+                                 {"XLATING_B200_LONG_FFMA2": "1", "XLATING_B200_LONG_TMAP": "0"},
+                                 {"XLATING_B200_LONG": "3"}, {"XLATING_B200_LONG": "2"}],
+                         ids=["default", "ffma2", "no_tmap", "ffma2_no_tmap", "long3", "long2"])
+def test_group_long_filter_odd_window_starts_and_variants(pkg, monkeypatch, env):
+    """configs[4] shape with ODD block lengths in between: the window start of the long-filter class changes
+    parity from block to block (the pipelined kernel then fetches its strips from one sample earlier; the
+    TMA tensor-map path, the strip path, the packed-FFMA2 arithmetic and the older kernel generations must all
+    give the oracle's answer), plus a ring wrap-around (the ring holds 5 blocks + history)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(6701)
+    fs, max_in = 61440000, 131072
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 9600)
+    g = pkg.Group(fs, max_in)
+    centers = [int(-30000000 + c * 2300000) for c in range(40)]  # two 32-client groups, the second partly padding
+    ids = [g.add_client(1280, taps, c) for c in centers]
+    check = [0, 7, 31, 32, 39]
+    oracles = {c: po.OracleFilter(1280, taps, centers[c], fs, max_in) for c in check}
+    sizes = [max_in, 50002, max_in, max_in, 30006, max_in, max_in, 131070, max_in, max_in, max_in, max_in]
+    for blk, n in enumerate(sizes):
+        x = rand_block(rng, "cs16", n)
+        t = g.submit("cs16", x)
+        g.wait(t)
+        for c in check:
+            assert_cf32_close(g.output(t, ids[c]), oracles[c].process_cf32("cs16", x), f"{env} blk {blk} c{c}")
+    assert {g.client_info(c)[1] for c in ids} == {2}
+    g.close()
+
+
 def test_group_rejects_oversized_block(pkg, capfd):
     """the reference overflows its work buffer here (src/xlating.c:353); we refuse"""
     g = pkg.Group(48000, 1000)
