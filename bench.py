@@ -516,7 +516,8 @@ def run_stream_leg(pkg, wl, args, rank, world, local_rank, steps, warmup, partit
     barrier()
     g.wait(last)
     n_out_total = sum(g.output_ptr(last, c)[1] for c in ids)
-    out = {"timed_window": (t_wall0, t_wall1), "n_out_total": n_out_total, "tapsets": tapsets}
+    out = {"timed_window": (t_wall0, t_wall1), "n_out_total": n_out_total, "tapsets": tapsets,
+           "partition_sms": g.partition_sms()}
 
     # ---- the last TIMED block, every sampled client, against the oracle
     if args.no_verify:
@@ -602,6 +603,28 @@ def run_stream_leg(pkg, wl, args, rank, world, local_rank, steps, warmup, partit
         g2.close()
         for p in pins:
             p.free()
+        # what bounds e2e: the D2H copy of every client's output.  Measure the copy engine's own ceiling on
+        # this box (pinned host buffer, same size as one step's results) and report the link's share.
+        try:
+            nbytes = int(min(max(n_out_total * 8 * STEP_BLOCKS, 64 << 20), 512 << 20))
+            d_buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            h_buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e30
+            for _ in range(4):
+                ev0.record()
+                h_buf.copy_(d_buf, non_blocking=True)
+                ev1.record()
+                ev1.synchronize()
+                best = min(best, ev0.elapsed_time(ev1))
+            peak = nbytes / (best * 1e-3) / 1e9
+            used = out["e2e"]["d2h_bytes_per_step"] / (out["e2e"]["ms_per_step"] * 1e-3) / 1e9
+            out["e2e"]["pcie"] = {"d2h_gbs": used, "d2h_peak_gbs": peak, "frac": used / peak,
+                                  "what": "bytes of results copied to the host per second of e2e wall clock, against a "
+                                          "plain pinned cudaMemcpy D2H of the same size measured in this run"}
+            del d_buf, h_buf
+        except Exception as e:  # noqa: BLE001
+            out["e2e"]["pcie"] = {"error": str(e)}
     return out
 
 
@@ -915,8 +938,11 @@ def main():
             "realtime_clients_per_gpu": int(main_leg["value"] / world * len(wl["plan"]) * 1e6 / wl["fs"]),
             "clocks": clocks, "roofline": roof,
             "engine": {"kernels_used": main_leg["kinds"], "taps_len": sorted({len(t) for t in main_leg["tapsets"].values()}),
-                       "sm_partition": ("off" if args.no_partition else
-                                        "8 SMs reserved for the oscillator pre-pass, FIR on the other 140 (green contexts)"),
+                       "sm_partition": ("off (--no-partition)" if args.no_partition else
+                                        f"{main_leg['partition_sms']} SMs reserved for the oscillator pre-pass (green contexts), "
+                                        "FIR on the others" if main_leg.get("partition_sms") else
+                                        "offered (XLG_SM_PARTITION) and declined for this layout: the oscillator chain is short "
+                                        "enough to share SMs with the FIR, which keeps all of them"),
                        "block_latency_us": main_leg["block_latency_us"], "host": main_leg["host"], "numa": numa}}
     if legs:
         line["legs"] = legs

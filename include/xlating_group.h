@@ -144,6 +144,11 @@ void xlg_free_pinned(void *p);
  * CUDA stream (e.g. the torch/NCCL stream that produced a device input). */
 int xlg_wait_stream(xlg_group *g, void *cuda_stream);
 
+/* SMs currently reserved for the oscillator pre-pass (0 = no partition active).  With XLG_SM_PARTITION the group
+ * decides per client layout whether the reservation pays (it does when the pre-pass chain would otherwise pace the
+ * pipeline); XLATING_B200_PARTITION=0/1 forces the answer. */
+int xlg_partition_active(xlg_group *g);
+
 /* Device-side timing of a region of submits: xlg_timer_start drains the group
  * and records a start event; xlg_timer_stop records an end event that depends
  * on all work submitted so far, synchronises and returns elapsed milliseconds. */

@@ -50,7 +50,7 @@ REFERENCE_SYMBOLS = (
 )
 GROUP_SYMBOLS = [
     "xlg_create", "xlg_create_ex", "xlg_destroy", "xlg_add_client", "xlg_add_client_ex", "xlg_remove_client", "xlg_reserve", "xlg_client_count", "xlg_submit",
-    "xlg_wait", "xlg_input_consumed", "xlg_output", "xlg_read_output", "xlg_copy_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_timer_start",
+    "xlg_wait", "xlg_input_consumed", "xlg_output", "xlg_read_output", "xlg_copy_output", "xlg_alloc_pinned", "xlg_free_pinned", "xlg_wait_stream", "xlg_partition_active", "xlg_timer_start",
     "xlg_timer_stop", "xlg_profile_enable", "xlg_profile_read", "xlg_client_info", "xlg_dropin_stats", "xlg_dropin_stream_stats", "xlg_dropin_stream_times",
 ]
 
@@ -126,6 +126,8 @@ def lib() -> C.CDLL:
     L.xlg_free_pinned.restype = None
     L.xlg_wait_stream.argtypes = [vp, vp]
     L.xlg_wait_stream.restype = C.c_int
+    L.xlg_partition_active.argtypes = [vp]
+    L.xlg_partition_active.restype = C.c_int
     L.xlg_timer_start.argtypes = [vp]
     L.xlg_timer_start.restype = C.c_int
     L.xlg_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -345,6 +347,10 @@ class Group:
         code = self._L.xlg_wait_stream(self._h, cuda_stream)
         if code != 0:
             raise RuntimeError(f"xlg_wait_stream -> {code}")
+
+    def partition_sms(self) -> int:
+        """SMs currently reserved for the oscillator pre-pass (0 = no partition active for this layout)."""
+        return int(self._L.xlg_partition_active(self._h))
 
     def timer_start(self) -> None:
         code = self._L.xlg_timer_start(self._h)

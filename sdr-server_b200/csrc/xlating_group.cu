@@ -216,6 +216,16 @@ struct xlg_group {
   cudaStream_t s_cs[kMaxCs] = {nullptr, nullptr, nullptr, nullptr};  // compute streams, round-robin by block
   int n_cs = 3;  // 3 measured 2.4 % faster than 2 on cfg2 (2129 vs 2079 MS/s), 4 no better
   SmPartition part;
+  // Two complete sets of pre-pass / conversion / compute streams: inside the green contexts (8 + 140 SMs) and
+  // ordinary ones (148 SMs).  s_ph / s_cv / s_cs alias the ACTIVE set; with XLG_SM_PARTITION the choice is made
+  // per layout (rebuild_layout: the partition pays only where the oscillator chain, ~5x slower when it shares SMs
+  // with FIR warps, would otherwise pace the pipeline), XLATING_B200_PARTITION=0/1 forces it.
+  struct StreamSet {
+    cudaStream_t ph = nullptr, cv = nullptr, cs[4] = {nullptr, nullptr, nullptr, nullptr};
+  } set_part, set_plain;
+  bool part_active = false;
+  int part_force = -1;    // -1 = automatic
+  int total_sms = 0;
 
   float2 *ring = nullptr;
   short2 *qring = nullptr;
@@ -332,9 +342,12 @@ static void slot_free(Slot &s) {
 
 static int drain(xlg_group *g) {
   CU_OK(cudaStreamSynchronize(g->s_in));
-  CU_OK(cudaStreamSynchronize(g->s_ph));
-  CU_OK(cudaStreamSynchronize(g->s_cv));
-  for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamSynchronize(g->s_cs[i]));
+  for (const xlg_group::StreamSet *ss : {&g->set_part, &g->set_plain}) {
+    if (ss->ph) CU_OK(cudaStreamSynchronize(ss->ph));
+    if (ss->cv) CU_OK(cudaStreamSynchronize(ss->cv));
+    for (cudaStream_t st : ss->cs)
+      if (st) CU_OK(cudaStreamSynchronize(st));
+  }
   CU_OK(cudaStreamSynchronize(g->s_out));
   return 0;
 }
@@ -483,6 +496,7 @@ static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
 // Re-derive everything that depends on the client set: output offsets, tap
 // arenas, kernel classes.  Dynamic per-client state (hist, phase) lives on the
 // device and is preserved.
+static void choose_partition(xlg_group *g);
 static int rebuild_layout(xlg_group *g) {
   if (drain(g)) return -EIO;
   const int nc = (int)g->clients.size();
@@ -885,8 +899,45 @@ static int rebuild_layout(xlg_group *g) {
       h.endph_cap = want;
     }
   }
+  choose_partition(g);
   g->dirty = false;
   return 0;
+}
+
+static void activate_streams(xlg_group *g, bool part) {
+  const xlg_group::StreamSet &ss = part ? g->set_part : g->set_plain;
+  g->s_ph = ss.ph;
+  g->s_cv = ss.cv;
+  for (int i = 0; i < xlg_group::kMaxCs; i++) g->s_cs[i] = ss.cs[i];
+  g->part_active = part;
+  g->fir_sms = part ? g->part.big_sms : g->total_sms;
+}
+
+// Partition or not, for the layout just built (the pipeline is drained).  Estimates per full-size block: the
+// oscillator chain alone (~6 us + 5.6 ns per output of the fastest client, measured 10.75 cycles per step) and
+// the FIR at the step-level efficiency the tiled kernels reach (0.76 x 36 TFMA/s).  Sharing SMs with FIR warps
+// the chain runs 4.6-6.7x slower (measured: c512 28 -> 130 us, 1000 clients 34 -> 225 us): if that still fits
+// inside the FIR time the 8 SMs are worth more as FIR SMs (1000 clients +4.4 %, configs[4] shard +5.2 %),
+// otherwise the chain would pace the pipeline and the partition wins (cfg2: 2156 vs 1590 MS/s).
+static void choose_partition(xlg_group *g) {
+  if (!g->part.ok) return;
+  bool want = true;
+  if (g->part_force >= 0) {
+    want = g->part_force != 0;
+  } else {
+    const double n = (double)(g->max_input_len / 2);
+    double steps = 0, fma = 0;
+    for (const HostClient &h : g->clients) {
+      if (!h.active) continue;
+      const double n_out = n / (double)h.D;
+      steps = std::max(steps, n_out);
+      fma += 4.0 * n_out * (double)h.T;
+    }
+    const double t_chain_us = 6.0 + steps * 0.0056 * 1.15;
+    const double t_fir_us = fma / (0.76 * 36.1e6) * (double)g->total_sms / (double)g->part.big_sms;
+    want = t_chain_us * 5.0 > t_fir_us;
+  }
+  if (want != g->part_active) activate_streams(g, want);
 }
 
 // Split the device into an 8-SM partition (oscillator pre-pass) and the rest (FIR)
@@ -932,9 +983,9 @@ static void partition_create(xlg_group *g, int device) {
   }
   g->part.small_sms = (int)small.sm.smCount;
   g->part.big_sms = (int)rest.sm.smCount;
-  g->s_ph = (cudaStream_t)st_ph;
-  g->s_cv = (cudaStream_t)st_cv;
-  for (int i = 0; i < xlg_group::kMaxCs; i++) g->s_cs[i] = (cudaStream_t)st_c[i];
+  g->set_part.ph = (cudaStream_t)st_ph;
+  g->set_part.cv = (cudaStream_t)st_cv;
+  for (int i = 0; i < xlg_group::kMaxCs; i++) g->set_part.cs[i] = (cudaStream_t)st_c[i];
   g->part.ok = true;
 }
 
@@ -1019,23 +1070,30 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     xlg_destroy(g);
     return code;
   };
+  g->total_sms = prop.multiProcessorCount;
   {
     bool want = (flags & XLG_SM_PARTITION) != 0;
     const char *pe = getenv("XLATING_B200_PARTITION");
-    if (pe != nullptr) want = atoi(pe) != 0;
+    if (pe != nullptr) {
+      want = atoi(pe) != 0;
+      g->part_force = want ? 1 : 0;
+    }
+    if (getenv("XLATING_B200_PARTITION_AUTO") != nullptr && atoi(getenv("XLATING_B200_PARTITION_AUTO")) == 0 && g->part_force < 0)
+      g->part_force = want ? 1 : 0;  // the flag means "always", as in round 1
     if (want) partition_create(g, device);
   }
   if (cudaStreamCreateWithFlags(&g->s_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&g->s_out, cudaStreamNonBlocking) != cudaSuccess)
     return fail(-EIO);
-  if (!g->part.ok) {
-    if (cudaStreamCreateWithFlags(&g->s_ph, cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
+  {
+    if (cudaStreamCreateWithFlags(&g->set_plain.ph, cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
     int prio_lo = 0, prio_hi = 0;  // "greatest" priority is the numerically lowest
     if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_lo = prio_hi = 0;
-    if (cudaStreamCreateWithPriority(&g->s_cv, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(-EIO);
+    if (cudaStreamCreateWithPriority(&g->set_plain.cv, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return fail(-EIO);
     for (int i = 0; i < xlg_group::kMaxCs; i++)
-      if (cudaStreamCreateWithFlags(&g->s_cs[i], cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
+      if (cudaStreamCreateWithFlags(&g->set_plain.cs[i], cudaStreamNonBlocking) != cudaSuccess) return fail(-EIO);
   }
+  activate_streams(g, g->part.ok);
   const size_t raw_bytes = (size_t)max_input_len * 2;  // cs16 worst case
   for (Slot &s : g->slots) {
     if (cudaMalloc(&s.d_raw, raw_bytes) != cudaSuccess) return fail(-ENOMEM);
@@ -1066,7 +1124,6 @@ extern "C" int xlg_create_ex(int device, uint32_t sampling_freq, uint32_t max_in
     if (sv != nullptr) g->speculate = atoi(sv) != 0;
     const char *cv = getenv("XLATING_B200_CSTREAMS");
     if (cv != nullptr) g->n_cs = std::min(std::max(atoi(cv), 1), (int)xlg_group::kMaxCs);
-    g->fir_sms = g->part.ok ? g->part.big_sms : prop.multiProcessorCount;
   }
   if (cudaFuncSetAttribute(fir_tile_cf32_kernel<32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileMaxSmem) !=
           cudaSuccess ||
@@ -1114,10 +1171,12 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g == nullptr) return;
   cudaSetDevice(g->device);
   if (g->s_in) cudaStreamSynchronize(g->s_in);
-  if (g->s_ph) cudaStreamSynchronize(g->s_ph);
-  if (g->s_cv) cudaStreamSynchronize(g->s_cv);
-  for (cudaStream_t st : g->s_cs)
-    if (st) cudaStreamSynchronize(st);
+  for (const xlg_group::StreamSet *ss : {&g->set_part, &g->set_plain}) {
+    if (ss->ph) cudaStreamSynchronize(ss->ph);
+    if (ss->cv) cudaStreamSynchronize(ss->cv);
+    for (cudaStream_t st : ss->cs)
+      if (st) cudaStreamSynchronize(st);
+  }
   if (g->s_out) cudaStreamSynchronize(g->s_out);
   if (g->timeline) {
     for (Slot &sl : g->slots)
@@ -1198,10 +1257,12 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_member_cid) cudaFree(g->d_member_cid);
   if (g->d_order) cudaFree(g->d_order);
   if (g->s_in) cudaStreamDestroy(g->s_in);
-  if (g->s_ph) cudaStreamDestroy(g->s_ph);
-  if (g->s_cv) cudaStreamDestroy(g->s_cv);
-  for (cudaStream_t st : g->s_cs)
-    if (st) cudaStreamDestroy(st);
+  for (const xlg_group::StreamSet *ss : {&g->set_part, &g->set_plain}) {
+    if (ss->ph) cudaStreamDestroy(ss->ph);
+    if (ss->cv) cudaStreamDestroy(ss->cv);
+    for (cudaStream_t st : ss->cs)
+      if (st) cudaStreamDestroy(st);
+  }
   if (g->s_out) cudaStreamDestroy(g->s_out);
   if (g->part.small_ctx || g->part.big_ctx) {
     pfn_cuGreenCtxDestroy p_destroy;
@@ -1886,11 +1947,19 @@ extern "C" int xlg_wait_stream(xlg_group *g, void *cuda_stream) {
   cudaEvent_t ev;
   CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU_OK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-  for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamWaitEvent(g->s_cs[i], ev, 0));
+  for (const xlg_group::StreamSet *ss : {&g->set_part, &g->set_plain}) {  // (the next layout may switch sets)
+    for (cudaStream_t st : ss->cs)
+      if (st) CU_OK(cudaStreamWaitEvent(st, ev, 0));
+    if (ss->cv) CU_OK(cudaStreamWaitEvent(ss->cv, ev, 0));
+  }
   CU_OK(cudaStreamWaitEvent(g->s_in, ev, 0));
-  CU_OK(cudaStreamWaitEvent(g->s_cv, ev, 0));
   CU_OK(cudaEventDestroy(ev));
   return 0;
+}
+
+extern "C" int xlg_partition_active(xlg_group *g) {
+  if (g == nullptr) return -EINVAL;
+  return g->part_active ? g->part.small_sms : 0;
 }
 
 extern "C" int xlg_timer_start(xlg_group *g) {

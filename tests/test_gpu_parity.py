@@ -420,6 +420,48 @@ def test_group_long_filter_odd_window_starts_and_variants(pkg, monkeypatch, env)
     g.close()
 
 
+def test_group_partition_is_chosen_per_layout(pkg, monkeypatch):
+    """XLG_SM_PARTITION offers the 8-SM oscillator partition; the group takes it where the pre-pass chain
+    would pace the pipeline (many outputs per block, little FIR work) and declines it where the FIR dominates
+    (configs[4] shape: 51 outputs per block, 15419 taps) -- and the answers do not depend on the choice."""
+    monkeypatch.delenv("XLATING_B200_PARTITION", raising=False)
+    rng = np.random.default_rng(6702)
+    # (a) chain-bound: 64 clients at 96 ksps from 2.016 Msps, 253 taps
+    fs, max_in = 2016000, 262144
+    taps = pkg.create_low_pass_filter(1.0, fs, 48000, 19200)
+    g = pkg.Group(fs, max_in, flags=pkg.XLG_SM_PARTITION)
+    centers = [int(-900000 + c * 28000) for c in range(64)]
+    ids = [g.add_client(21, taps, c) for c in centers]
+    oracles = {c: po.OracleFilter(21, taps, centers[c], fs, max_in) for c in (0, 33, 63)}
+    for blk in range(3):
+        x = rand_block(rng, "cu8", max_in)
+        t = g.submit("cu8", x)
+        g.wait(t)
+        for c, o in oracles.items():
+            assert_cf32_close(g.output(t, ids[c]), o.process_cf32("cu8", x), f"(a) blk {blk} c{c}")
+    sms_a = g.partition_sms()
+    g.close()
+    # (b) FIR-bound: 384 clients with the configs[4] filter
+    fs, max_in = 61440000, 131072
+    taps = pkg.create_low_pass_filter(1.0, fs, 24000, 9600)
+    g = pkg.Group(fs, max_in, flags=pkg.XLG_SM_PARTITION)
+    centers = [int(-30000000 + c * 150000) for c in range(384)]
+    ids = [g.add_client(1280, taps, c) for c in centers]
+    oracles = {c: po.OracleFilter(1280, taps, centers[c], fs, max_in) for c in (0, 200, 383)}
+    for blk in range(3):
+        x = rand_block(rng, "cs16", max_in)
+        t = g.submit("cs16", x)
+        g.wait(t)
+        for c, o in oracles.items():
+            assert_cf32_close(g.output(t, ids[c]), o.process_cf32("cs16", x), f"(b) blk {blk} c{c}")
+    sms_b = g.partition_sms()
+    g.close()
+    # green contexts may be unavailable on a driver (then both are 0 and the group said so in its log)
+    assert sms_a in (0, 8) and sms_b == 0, (sms_a, sms_b)
+    if sms_a == 0:
+        pytest.skip("green contexts unavailable: the partition could not be offered")
+
+
 def test_group_rejects_oversized_block(pkg, capfd):
     """the reference overflows its work buffer here (src/xlating.c:353); we refuse"""
     g = pkg.Group(48000, 1000)
