@@ -180,6 +180,18 @@ int main(int argc, char **argv) {
     run<16, 4, 8, 2, false, 8>("occ_16x4x8_scalar", per_sm, passes, d_out, sms, mhz);
     run<16, 4, 8, 2, true, 8>("occ_16x4x8_packed", per_sm, passes, d_out, sms, mhz);
   }
+  // other thread tiles at production occupancy (4 CTAs x 2 warps)
+  run<16, 3, 8, 2, false, 4>("t_16x3x8", 4, passes, d_out, sms, mhz);
+  run<16, 5, 8, 2, false, 4>("t_16x5x8", 4, passes, d_out, sms, mhz);
+  run<16, 6, 8, 2, false, 4>("t_16x6x8", 4, passes, d_out, sms, mhz);
+  run<8, 6, 8, 2, false, 4>("t_8x6x8", 4, passes, d_out, sms, mhz);
+  run<8, 7, 8, 2, false, 4>("t_8x7x8", 4, passes, d_out, sms, mhz);
+  run<4, 7, 8, 2, false, 4>("t_4x7x8", 4, passes, d_out, sms, mhz);
+  run<4, 7, 8, 8, false, 1>("t_4x7x8_8warps_long4", 1, passes, d_out, sms, mhz);
+  run<16, 4, 4, 2, false, 4>("t_16x4x4", 4, passes, d_out, sms, mhz);
+  run<16, 4, 12, 2, false, 4>("t_16x4x12", 4, passes, d_out, sms, mhz);
+  run<16, 6, 4, 2, false, 4>("t_16x6x4", 4, passes, d_out, sms, mhz);
+  run<16, 8, 4, 2, false, 4>("t_16x8x4", 4, passes, d_out, sms, mhz);
   for (int per_sm = 2; per_sm <= 4; per_sm += 2) {
     run<16, 4, 8, 2, false, 4>("cur_16x4x8_scalar", per_sm, passes, d_out, sms, mhz);
     run<16, 4, 8, 2, true, 4>("cur_16x4x8_packed", per_sm, passes, d_out, sms, mhz);
