@@ -1524,7 +1524,8 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     CU_OK(cudaEventRecord(s.ev_conv, cvs));
   }
   // the FIR reads this block's samples and, as history, the previous blocks'
-  if (g->have_last_conv) CU_OK(cudaStreamWaitEvent(cs, g->ev_last_conv_ref, 0));
+  // (s_cv is in order: waiting for THIS block's conversion covers the earlier ones -- one driver call less)
+  if (g->have_last_conv && (cvs == cs || n == 0)) CU_OK(cudaStreamWaitEvent(cs, g->ev_last_conv_ref, 0));
   if (n > 0) {
     if (cvs != cs) CU_OK(cudaStreamWaitEvent(cs, s.ev_conv, 0));
     g->ev_last_conv_ref = s.ev_conv;
@@ -1793,8 +1794,7 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
       CU_OK(cudaMemcpyAsync(ho.h_endph, s.d_endph, (size_t)nc * sizeof(float2), cudaMemcpyDeviceToHost, g->s_out));
     CU_OK(cudaEventRecord(s.ev_done, g->s_out));
   } else {
-    CU_OK(cudaStreamWaitEvent(g->s_out, s.ev_fir, 0));
-    CU_OK(cudaEventRecord(s.ev_done, g->s_out));
+    CU_OK(cudaEventRecord(s.ev_done, cs));  // results stay on the device: done = FIR done, no hop through s_out
   }
 
   if (q15)
