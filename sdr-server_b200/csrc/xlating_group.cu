@@ -252,6 +252,9 @@ struct xlg_group {
   float2 *d_taps = nullptr;
   short2 *d_qtaps = nullptr;
   void *d_tile_taps = nullptr;
+  std::vector<float2> h_taps, h_tile_taps;  // host staging of the tap arenas, kept between re-layouts (no fresh pages)
+  std::vector<short2> h_qtaps;
+  size_t cap_taps = 0, cap_qtaps = 0, cap_tile_taps = 0, cap_members = 0, cap_member_cid = 0, cap_member_incr = 0;
   int tile_force = 0;     // XLATING_B200_TILE=<LO*10+RK> pins the tile shape (e.g. 324, 164, 162, 161)
   int long_kt = W2_KT;    // output tile of the long-filter kernel: 56 (fir_long3 / fir_long2) or 64 (XLATING_B200_LONG=1)
   // long4's input strips through a TMA tensor map over the ring (XLATING_B200_LONG_TMAP=0: 28 bulk copies per stage)
@@ -497,8 +500,35 @@ static int ensure_arenas(xlg_group *g, size_t need, bool need_q) {
 // arenas, kernel classes.  Dynamic per-client state (hist, phase) lives on the
 // device and is preserved.
 static void choose_partition(xlg_group *g);
+// (re)fill a device array; the allocation is reused while it is large enough (a re-layout per attach must not
+// pay a cudaFree + cudaMalloc -- each an implicit device synchronisation -- for every table)
+template <typename T>
+static int dev_assign(T **dptr, size_t *cap_bytes, const void *src, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (*dptr == nullptr || *cap_bytes < bytes) {
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    const size_t want = bytes + bytes / 4 + 4096;
+    CU_OK(cudaMalloc(dptr, want));
+    *cap_bytes = want;
+  }
+  CU_OK(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
 static int rebuild_layout(xlg_group *g) {
+  // XLATING_B200_REBUILD_TIMING=1: where a re-layout spends its time (logged per call)
+  static const bool timing = getenv("XLATING_B200_REBUILD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  double t_stage[6] = {0, 0, 0, 0, 0, 0};
+  auto tick = [&](int i) {
+    const auto now = std::chrono::steady_clock::now();
+    t_stage[i] += std::chrono::duration<double, std::micro>(now - t_prev).count();
+    t_prev = now;
+  };
   if (drain(g)) return -EIO;
+  tick(0);
+  const bool env_skewed = getenv("XLATING_B200_SKEWED") != nullptr, env_no_long = getenv("XLATING_B200_NO_LONG") != nullptr,
+             env_no_merge = getenv("XLATING_B200_NO_MERGE") != nullptr;
   const int nc = (int)g->clients.size();
   g->max_client = 0;
   for (int i = 0; i < nc; i++)
@@ -528,25 +558,21 @@ static int rebuild_layout(xlg_group *g) {
   if (ensure_ring(g, max_hist, g->qring != nullptr)) return -EIO;
   if (ensure_arenas(g, out_total, g->q_alloc)) return -EIO;
 
-  std::vector<float2> taps(std::max<size_t>(taps_total, 1));
-  std::vector<short2> qtaps(std::max<size_t>(taps_total, 1));
+  std::vector<float2> &taps = g->h_taps;
+  std::vector<short2> &qtaps = g->h_qtaps;
+  taps.resize(std::max<size_t>(taps_total, 1));
+  qtaps.resize(std::max<size_t>(taps_total, 1));
   for (int i = 0; i < nc; i++) {
     const HostClient &h = g->clients[i];
     if (!h.active) continue;
-    for (size_t j = 0; j < h.T; j++) {
-      taps[h.taps_off + j] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
-      qtaps[h.taps_off + j] = make_short2(h.rev_q15[2 * j], h.rev_q15[2 * j + 1]);
-    }
+    memcpy(&taps[h.taps_off], h.rev.data(), h.T * sizeof(float2));        // both interleaved (re, im)
+    memcpy(&qtaps[h.taps_off], h.rev_q15.data(), h.T * sizeof(short2));
   }
-  if (g->d_taps) cudaFree(g->d_taps);
-  if (g->d_qtaps) cudaFree(g->d_qtaps);
-  g->d_taps = nullptr;
-  g->d_qtaps = nullptr;
-  CU_OK(cudaMalloc(&g->d_taps, taps.size() * sizeof(float2)));
-  CU_OK(cudaMalloc(&g->d_qtaps, qtaps.size() * sizeof(short2)));
-  CU_OK(cudaMemcpy(g->d_taps, taps.data(), taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  CU_OK(cudaMemcpy(g->d_qtaps, qtaps.data(), qtaps.size() * sizeof(short2), cudaMemcpyHostToDevice));
+  if (dev_assign(&g->d_taps, &g->cap_taps, taps.data(), taps.size() * sizeof(float2)) ||
+      dev_assign(&g->d_qtaps, &g->cap_qtaps, qtaps.data(), qtaps.size() * sizeof(short2)))
+    return -EIO;
 
+  tick(1);
   // 3. classes for the tiled / long-filter kernels.  A class is a set of clients with
   //    the same (D, T) whose zero-history window has passed (zero_before behind the
   //    next window start, or the stream origin where the ring itself is still zero).
@@ -567,14 +593,14 @@ static int rebuild_layout(xlg_group *g) {
   auto mode_of = [&](uint32_t D, size_t T) {
     Mode m;
     const unsigned g16 = (D % 16 == 0) ? 16u : (D % 8 == 0) ? 8u : (D % 4 == 0) ? 4u : (D % 2 == 0) ? 2u : 1u;
-    m.natural = g16 <= 2 && !getenv("XLATING_B200_SKEWED");
+    m.natural = g16 <= 2 && !env_skewed;
     m.Dp = m.natural ? (int)D : (int)(D | 1u);
     const size_t q_last = (T - 1) / D, r_last = (T - 1) % D;
     m.L = (int)(((q_last * m.Dp + r_last + 1) + 7) / 8 * 8);
     const size_t smem = smem_fixed + ((size_t)(KT - 1) * m.Dp + m.L + D + 10) * sizeof(float2);
     const size_t typical_out = g->max_input_len / 2 / D;
     // too long for a shared-memory tile -> split-K long-filter class (natural layout)
-    m.as_long = smem > (size_t)kTileMaxSmem && typical_out >= 1 && !getenv("XLATING_B200_NO_LONG");
+    m.as_long = smem > (size_t)kTileMaxSmem && typical_out >= 1 && !env_no_long;
     m.eligible = m.as_long || (smem <= (size_t)kTileMaxSmem && typical_out >= (size_t)kTileMinOutputs);
     if (m.as_long) {
       m.natural = true;
@@ -602,7 +628,7 @@ static int rebuild_layout(xlg_group *g) {
       h.pending_settle = true;  // re-derive the layout once its window has passed
       continue;
     }
-    const bool merge = m.natural && !m.as_long && !getenv("XLATING_B200_NO_MERGE");
+    const bool merge = m.natural && !m.as_long && !env_no_merge;
     buckets[std::make_tuple(h.D, h.T, merge ? -1ll : h.hist)].push_back(i);
   }
   {
@@ -614,7 +640,8 @@ static int rebuild_layout(xlg_group *g) {
   std::vector<int> members;       // output row offset per member slot
   std::vector<int> member_cid;    // client id per member slot
   std::vector<float2> member_incr;
-  std::vector<float2> tile_taps;
+  std::vector<float2> &tile_taps = g->h_tile_taps;
+  tile_taps.clear();
   for (auto &kv : buckets) {
     const uint32_t D = std::get<0>(kv.first);
     const size_t T = std::get<1>(kv.first);
@@ -673,50 +700,58 @@ static int rebuild_layout(xlg_group *g) {
       members.push_back(h.out_off);
       member_incr.push_back(make_float2(h.incr_re, h.incr_im));
       h.kind = m.as_long ? 2 : 1;
-      const size_t gi = sl / T_CG, mslot = sl % T_CG;
+    }
+    // taps into [group][flat tap f][32 slots]: one 256-byte line (all 32 slots of a tap) at a time -- slot-major
+    // packing touched a new cache line for every tap of every client (1.5 ms per re-layout at 1000 clients)
+    const bool pk = m.as_long ? g->long_pk_active : g->packed;
+    for (size_t gi = 0; gi < slots.size() / T_CG; gi++) {
       float2 *dst = tile_taps.data() + base + gi * (size_t)m.L * T_CG;
-      if (m.as_long ? g->long_pk_active : g->packed) {
-        // packed kernel: a client PAIR's tap is (re0, re1, im0, im1) -- one 128-bit load = two FFMA2 operands
-        float *dq = reinterpret_cast<float *>(dst);
-        const size_t pair = mslot / 2, e = mslot % 2;
-        for (size_t j = 0; j < T; j++) {
-          const size_t f = (j / D) * m.Dp + (j % D);
-          float *q4 = dq + (f * T_CG + 2 * pair) * 2;
-          q4[e] = h.rev[2 * j];
-          q4[2 + e] = h.rev[2 * j + 1];
+      const float *src[T_CG];
+      for (int sl = 0; sl < T_CG; sl++) {
+        const int id = slots[gi * T_CG + sl];
+        src[sl] = id < 0 ? nullptr : g->clients[id].rev.data();
+      }
+      size_t q = 0, r = 0;  // j = q * D + r
+      for (size_t j = 0; j < T; j++) {
+        const size_t f = q * m.Dp + r;
+        if (++r == D) {
+          r = 0;
+          q++;
         }
-      } else {
-        for (size_t j = 0; j < T; j++) {
-          const size_t f = (j / D) * m.Dp + (j % D);
-          dst[f * T_CG + mslot] = make_float2(h.rev[2 * j], h.rev[2 * j + 1]);
+        if (pk) {
+          // packed kernel: a client PAIR's tap is (re0, re1, im0, im1) -- one 128-bit load = two FFMA2 operands
+          float *row = reinterpret_cast<float *>(dst + f * T_CG);
+          for (int sl = 0; sl < T_CG; sl++)
+            if (src[sl]) {
+              float *q4 = row + (sl & ~1) * 2;
+              q4[sl & 1] = src[sl][2 * j];
+              q4[2 + (sl & 1)] = src[sl][2 * j + 1];
+            }
+        } else {
+          float2 *row = dst + f * T_CG;
+          for (int sl = 0; sl < T_CG; sl++)
+            if (src[sl]) row[sl] = make_float2(src[sl][2 * j], src[sl][2 * j + 1]);
         }
       }
     }
     dest.push_back(ch);
   }
+  tick(2);
   // heaviest classes first: their CTAs are scheduled first and the lighter ones
   // fill the tail of the launch
   std::sort(g->classes.begin(), g->classes.end(), [](const TileClassHost &a, const TileClassHost &b) {
     return a.k.L > b.k.L;
   });
-  if (g->d_tile_taps) cudaFree(g->d_tile_taps);
-  if (g->d_members) cudaFree(g->d_members);
-  if (g->d_member_incr) cudaFree(g->d_member_incr);
-  if (g->d_member_cid) cudaFree(g->d_member_cid);
-  g->d_tile_taps = nullptr;
-  g->d_members = nullptr;
-  g->d_member_incr = nullptr;
-  g->d_member_cid = nullptr;
   if (!tile_taps.empty()) {
-    CU_OK(cudaMalloc(&g->d_tile_taps, tile_taps.size() * sizeof(float2)));
-    CU_OK(cudaMemcpy(g->d_tile_taps, tile_taps.data(), tile_taps.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    CU_OK(cudaMalloc(&g->d_members, members.size() * sizeof(int)));
-    CU_OK(cudaMemcpy(g->d_members, members.data(), members.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU_OK(cudaMalloc(&g->d_member_cid, member_cid.size() * sizeof(int)));
-    CU_OK(cudaMemcpy(g->d_member_cid, member_cid.data(), member_cid.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU_OK(cudaMalloc(&g->d_member_incr, member_incr.size() * sizeof(float2)));
-    CU_OK(cudaMemcpy(g->d_member_incr, member_incr.data(), member_incr.size() * sizeof(float2),
-                     cudaMemcpyHostToDevice));
+    void *tt = g->d_tile_taps;
+    if (dev_assign(&tt, &g->cap_tile_taps, tile_taps.data(), tile_taps.size() * sizeof(float2)) ||
+        dev_assign(&g->d_members, &g->cap_members, members.data(), members.size() * sizeof(int)) ||
+        dev_assign(&g->d_member_cid, &g->cap_member_cid, member_cid.data(), member_cid.size() * sizeof(int)) ||
+        dev_assign(&g->d_member_incr, &g->cap_member_incr, member_incr.data(), member_incr.size() * sizeof(float2))) {
+      g->d_tile_taps = tt;
+      return -EIO;
+    }
+    g->d_tile_taps = tt;
   }
 
   // 3a. long filters: every 256 KiB block streams ALL their taps once (each tap serves only ~52
@@ -748,6 +783,7 @@ static int rebuild_layout(xlg_group *g) {
     }
   }
 
+  tick(3);
   // 3b. oscillator-table order: tile classes (the order the tiled kernel walks them),
   //     then generic clients; 32 clients per table group
   {
@@ -901,6 +937,10 @@ static int rebuild_layout(xlg_group *g) {
   }
   choose_partition(g);
   g->dirty = false;
+  tick(4);
+  if (timing)
+    XL_LOG("re-layout of %d clients: drain %.0f us, state + natural taps %.0f, classes + packing %.0f, tile uploads %.0f, "
+           "tables + arenas %.0f", nc, t_stage[0], t_stage[1], t_stage[2], t_stage[3], t_stage[4]);
   return 0;
 }
 
