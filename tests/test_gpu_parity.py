@@ -184,8 +184,15 @@ def test_group_mixed_clients_vs_oracle(pkg, fmt, flags):
     g.close()
 
 
-def test_group_pipelined_tickets(pkg):
-    """XLG_SLOTS blocks in flight before the first wait; outputs stay valid."""
+@pytest.mark.parametrize("env", [{}, {"XLATING_B200_CONV_STREAM": "0"}, {"XLATING_B200_FFMA2": "1"},
+                                 {"XLATING_B200_SPECULATE": "0", "XLATING_B200_CSTREAMS": "1"},
+                                 {"XLATING_B200_PARTITION": "1"}, {"XLATING_B200_PARTITION": "0"}],
+                         ids=["default", "conv_on_compute_stream", "ffma2", "no_spec_1stream", "partition", "no_partition"])
+def test_group_pipelined_tickets(pkg, monkeypatch, env):
+    """XLG_SLOTS blocks in flight before the first wait; outputs stay valid -- in every pipeline variant the
+    measurement switches select (conversion stream, packed arithmetic, speculation, stream count, SM partition)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     rng = np.random.default_rng(13)
     fs, max_in = 2016000, 32768
     plan = pkg.client_plan(fs, [48000] * 16, tw=16400)
