@@ -210,6 +210,8 @@ struct xlg_group {
   cudaStream_t s_in = nullptr, s_ph = nullptr, s_out = nullptr;
   // raw -> ring conversion: its own stream, in the oscillator partition (or at high priority without one), so
   // that block b+1's conversion never queues behind the CTAs of block b's FIR that are still waiting for an SM
+  cudaEvent_t ev_user = nullptr;  // xlg_wait_stream: recorded on the caller's stream, waited for by the next submit's first reader
+  bool user_wait_pending = false;
   cudaStream_t s_cv = nullptr;
   bool conv_own_stream = true;  // XLATING_B200_CONV_STREAM=0: convert on the block's compute stream (the old order)
   static constexpr int kMaxCs = 4;
@@ -1296,6 +1298,7 @@ extern "C" void xlg_destroy(xlg_group *g) {
   if (g->d_member_incr) cudaFree(g->d_member_incr);
   if (g->d_member_cid) cudaFree(g->d_member_cid);
   if (g->d_order) cudaFree(g->d_order);
+  if (g->ev_user) cudaEventDestroy(g->ev_user);
   if (g->s_in) cudaStreamDestroy(g->s_in);
   for (const xlg_group::StreamSet *ss : {&g->set_part, &g->set_plain}) {
     if (ss->ph) cudaStreamDestroy(ss->ph);
@@ -1543,6 +1546,14 @@ extern "C" int64_t xlg_submit(xlg_group *g, int fmt, const void *input, size_t i
     d_in = s.d_raw;
   }
 
+  if (g->user_wait_pending) {
+    // (in-order streams: later submits' conversions queue behind this one's, so one wait is enough)
+    CU_OK(cudaStreamWaitEvent(cvs, g->ev_user, 0));
+    CU_OK(cudaStreamWaitEvent(g->s_in, g->ev_user, 0));
+    if (!g->conv_own_stream)
+      for (int i = 0; i < g->n_cs; i++) CU_OK(cudaStreamWaitEvent(g->s_cs[i], g->ev_user, 0));
+    g->user_wait_pending = false;
+  }
   // ---- convert (its own stream: never behind the FIR CTAs of earlier blocks that still wait for an SM) ----
   s.pf_conv = s.pf_phase = s.pf_tile = s.pf_gen = false;
   if (n > 0) {
@@ -1984,16 +1995,13 @@ extern "C" void xlg_free_pinned(void *p) {
 extern "C" int xlg_wait_stream(xlg_group *g, void *cuda_stream) {
   if (g == nullptr) return -EINVAL;
   cudaSetDevice(g->device);
-  cudaEvent_t ev;
-  CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CU_OK(cudaEventRecord(ev, (cudaStream_t)cuda_stream));
-  for (const xlg_group::StreamSet *ss : {&g->set_part, &g->set_plain}) {  // (the next layout may switch sets)
-    for (cudaStream_t st : ss->cs)
-      if (st) CU_OK(cudaStreamWaitEvent(st, ev, 0));
-    if (ss->cv) CU_OK(cudaStreamWaitEvent(ss->cv, ev, 0));
-  }
-  CU_OK(cudaStreamWaitEvent(g->s_in, ev, 0));
-  CU_OK(cudaEventDestroy(ev));
+  // Only the first reader of a device-resident input has to wait: the conversion (and the H2D stream, for
+  // symmetry with host inputs).  The event is recorded now and attached to the consuming stream by the next
+  // xlg_submit -- which knows the stream (a re-layout in between may switch stream sets) -- so a call costs one
+  // record here and one wait there instead of a wait on every stream of the group.
+  if (g->ev_user == nullptr) CU_OK(cudaEventCreateWithFlags(&g->ev_user, cudaEventDisableTiming));
+  CU_OK(cudaEventRecord(g->ev_user, (cudaStream_t)cuda_stream));
+  g->user_wait_pending = true;
   return 0;
 }
 
