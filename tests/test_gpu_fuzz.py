@@ -37,8 +37,11 @@ def test_random_scenarios(pkg, seed):
     taps_by_d = {}
     for d in DECIMS:
         if rng.random() < 0.3:
-            t = int(rng.integers(31, 400))
-            taps_by_d[d] = (rng.standard_normal(t) * 0.05).astype(np.float32)  # arbitrary (also even) lengths
+            # arbitrary (also even) lengths, but never shorter than the decimation: with D > T the reference's
+            # history_offset underflows (src/xlating.c:76, undefined behaviour -- the oracle, a faithful
+            # restatement, crashes there too; lpf.c never produces such taps)
+            t = int(rng.integers(max(31, d + 1), 400))
+            taps_by_d[d] = (rng.standard_normal(t) * 0.05).astype(np.float32)
         else:
             taps_by_d[d] = pkg.create_low_pass_filter(1.0, fs, fs // d // 2, max(fs // d // int(rng.integers(3, 12)), 50))
     long_d = None
