@@ -469,6 +469,47 @@ def test_group_partition_is_chosen_per_layout(pkg, monkeypatch):
         pytest.skip("green contexts unavailable: the partition could not be offered")
 
 
+def test_decimation_larger_than_the_filter_is_defined_here(pkg):
+    """D > T: in the reference `history_offset` underflows (src/xlating.c:76, undefined behaviour; its oracle
+    restatement crashes there as well), so there is nothing to be bit-identical with.  Here the decimator simply
+    skips the samples between windows.  Checked against the definition itself in float64,
+        y[k] = p^k * sum_j x[k*D + j - (T-1)] * rev[j],   x = 0 before the stream starts,
+    through the batch ABI and the per-filter ABI, over ragged blocks."""
+    rng = np.random.default_rng(6703)
+    fs, max_in = 2400000, 8192
+    for D, T in ((48, 39), (100, 31)):
+        taps = (rng.standard_normal(T) * 0.05).astype(np.float32)
+        center = 123000
+        w0 = np.float32(2 * np.pi * center / fs)
+        bpf = taps.astype(np.complex128) * np.exp(1j * (np.arange(T, dtype=np.float32) * w0).astype(np.float64))
+        rev = bpf[::-1]
+        if T % 2 == 0:  # the reference re-swaps the middle pair of an even-length vector (src/xlating.c:530-534)
+            a, b = T // 2 - 1, T // 2
+            rev[a], rev[b] = rev[b], rev[a]
+        # the oscillator step as the reference forms it: float product, cexpf, float components (src/xlating.c:544)
+        inc = complex(np.complex64(np.exp(1j * np.float64(np.float32(-w0 * np.float32(D))))))
+        g = pkg.Group(fs, max_in)
+        cid = g.add_client(D, taps, center)
+        f = pkg.XlatingFilter(D, taps, center, fs, max_in)
+        xs, got_g, got_f = [], [], []
+        for n in (max_in, 1000, 2, max_in, 4098, 600, max_in):
+            raw = rand_block(rng, "cu8", n)
+            t = g.submit("cu8", raw)
+            g.wait(t)
+            got_g.append(np.array(g.output(t, cid)))
+            got_f.append(np.array(f.process_cf32("cu8", raw)))
+            xs.append((raw.astype(np.float64)[0::2] - 127.5) / 128.0 + 1j * (raw.astype(np.float64)[1::2] - 127.5) / 128.0)
+        x = np.concatenate([np.zeros(T - 1, dtype=np.complex128)] + xs)
+        n_out = (len(x) - T) // D + 1
+        ref = np.array([np.dot(x[k * D:k * D + T], rev) for k in range(n_out)]) * inc ** np.arange(n_out)
+        for name, got in (("batch", np.concatenate(got_g)), ("per-filter", np.concatenate(got_f))):
+            assert got.shape == ref.shape, f"D={D} T={T} {name}: {got.shape} outputs, definition {ref.shape}"
+            err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+            assert err < 1e-4, f"D={D} T={T} {name}: {err:.2e} from the definition"
+        g.close()
+        f.close()
+
+
 def test_group_rejects_oversized_block(pkg, capfd):
     """the reference overflows its work buffer here (src/xlating.c:353); we refuse"""
     g = pkg.Group(48000, 1000)
