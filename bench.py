@@ -923,6 +923,23 @@ def main():
                                                "streams): algorithmic FMAs of a block / device time per block"},
                         "note": "this path is bound by the FP32 FMA pipe, not HBM (DESIGN.md section 4); kernel_ms is "
                                 "the kernel alone (non-overlapped pass, CUDA events on its stream)"}
+        # what actually binds, in one place: neither HBM nor the tensor pipe but the FP32 FMA pipe -- and of that, the
+        # share a shared-memory-fed FFMA loop can reach at all: this kernel's inner loop alone on data already in shared
+        # memory, measured in this run (tools/tilebench.cu; all 20 tile shapes: profiles/r2_tilebench.jsonl)
+        ceiling, ceiling_src = None, "tools/bin/tilebench not available"
+        try:
+            outp = subprocess.run([os.path.join(ROOT, "tools", "bin", "tilebench"), "400", "prod"],
+                                  capture_output=True, text=True, timeout=60).stdout
+            ceiling = max(json.loads(ln)["tfma_per_s"] for ln in outp.splitlines() if '"cur_16x4x8_scalar"' in ln) / fp32_peak
+            ceiling_src = "tools/bin/tilebench 400 prod, measured in this run, / the microbench peak"
+        except Exception:  # noqa: BLE001
+            pass
+        roof["binding"] = {"pipe": "fp32_fma", "frac_kernel_alone": roof["fp32"]["frac"],
+                           "frac_step": roof["fp32"]["step_level"]["frac"],
+                           "loop_ceiling_frac": ceiling, "loop_ceiling_source": ceiling_src,
+                           "note": "loop_ceiling = the tiled kernel's inner loop with its operands already in shared "
+                                   "memory (no TMA, barriers, epilogue) on all SMs; the step runs on the SMs left of the "
+                                   "oscillator partition"}
     roof["step_kernels_ms"] = {k: prof[f"{k}_ms"] / max(prof[f"{k}_launches"], 1)
                                for k in ("convert", "phase", "fir_tile", "fir_long", "fir_generic")}
 

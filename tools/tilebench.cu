@@ -8,7 +8,7 @@
  *   warp tile = (LO*RK) outputs x (32/LO*RC) clients; W warps per CTA split the clients.
  *
  * Per tap a thread loads RK x-values (LDS.64) and RC taps (RC/2 LDS.128) for 4*RK*RC FMAs.
- * Prints FMA/clk/SM from CUDA-event time and the SM clock.  Usage: tilebench [passes]
+ * Prints FMA/clk/SM from CUDA-event time and the SM clock.  Usage: tilebench [passes [prod]]
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -176,6 +176,10 @@ int main(int argc, char **argv) {
   float *d_out;
   cudaMalloc(&d_out, sizeof(float) * 148 * 8 * 256);
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_mhz\": %.0f}\n", prop.name, sms, mhz);
+  if (argc > 2) {  // `tilebench <passes> prod`: the production tile at production occupancy only (bench.py's loop ceiling)
+    run<16, 4, 8, 2, false, 4>("cur_16x4x8_scalar", 4, passes, d_out, sms, mhz);
+    return 0;
+  }
   for (int per_sm = 5; per_sm <= 8; per_sm++) {  // more resident warps than production's 8 per SM
     run<16, 4, 8, 2, false, 8>("occ_16x4x8_scalar", per_sm, passes, d_out, sms, mhz);
     run<16, 4, 8, 2, true, 8>("occ_16x4x8_packed", per_sm, passes, d_out, sms, mhz);
